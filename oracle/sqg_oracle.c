@@ -1,0 +1,403 @@
+/* oracle/sqg_oracle.c — TEST INFRASTRUCTURE ONLY (see sqg_oracle.h).
+ *
+ * CPU restatement of the squigulator signal-generation hot path.  Every function cites the
+ * reference file:line it follows (paths relative to /root/reference).  Nothing here is shipped:
+ * the product (squigulator_b200/csrc) never links, imports or executes this file.
+ *
+ * Parity status: PINNED.  Legacy mode reproduces the reference's golden .exp files bit for bit
+ * (tests/test_oracle_golden.py, fixtures in tests/golden/ made by scripts/make_golden.py from the
+ * reference built unmodified into oracle/_ref/), and equals oracle/_ref/libsqref.so on random
+ * inputs (tests/test_oracle_vs_ref.py).  Philox mode shares every non-RNG line with legacy mode.
+ *
+ * Compile with -ffp-contract=off (oracle/Makefile): no expression below may be fused.
+ */
+#include "sqg_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ k-mer ranks */
+
+/* src/seq.h:14-28: IUPAC folding; anything unknown (incl. N and NUL) ranks as A */
+static uint32_t base_rank4(char b) {
+    switch (b) {
+        case 'A': case 'a': case 'R': case 'W': case 'M': case 'D': case 'H': case 'V': return 0;
+        case 'C': case 'c': case 'Y': case 'B': return 1;
+        case 'G': case 'g': case 'S': case 'K': return 2;
+        case 'T': case 't': case 'U': return 3;
+        default: return 0;
+    }
+}
+
+/* src/seq.h:45-60: upper-case A,C,G,M,T only */
+static uint32_t base_rank5(char b) {
+    switch (b) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'M': return 3;
+        case 'T': return 4;
+        default: return 0;
+    }
+}
+
+/* src/seq.h:31-42: first base is the most significant 2-bit digit */
+uint32_t sqo_kmer_rank(const char *s, uint32_t k) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < k; i++) r = (r << 2) | base_rank4(s[i]);
+    return r;
+}
+
+/* src/seq.h:62-74: first base is the most significant base-5 digit */
+uint32_t sqo_meth_kmer_rank(const char *s, uint32_t k) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < k; i++) r = r * 5 + base_rank5(s[i]);
+    return r;
+}
+
+/* ------------------------------------------------------------------ legacy RNG (src/rand.h) */
+
+/* src/rand.h:79-85: Schrage minstd step; the UN-normalised value is what is stored back */
+double sqo_lehmer_next(int64_t *state) {
+    int64_t x = *state;
+    int64_t hi = x / 127773, lo = x % 127773;
+    int64_t nx = 16807 * lo - 2836 * hi;
+    *state = nx;
+    if (nx <= 0) nx += 2147483647;
+    return (double)nx / 2147483647;
+}
+
+/* src/rand.h:87-94: Box-Muller, cosine branch, truncated pi literal, exactly two uniforms */
+double sqo_lehmer_normal(int64_t *state, double m, double s) {
+    double u = sqo_lehmer_next(state);
+    double t = 2.0 * 3.14159265 * sqo_lehmer_next(state);
+    double x = sqrt(-2.0 * log(u)) * cos(t);
+    return x * s + m;
+}
+
+/* ------------------------------------------------------------------ Philox4x32-10 */
+
+void sqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* counter word 3 = stream tag */
+enum { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
+
+#define Z1_N 32768
+#define Z_TAIL_FIRST 32752
+#define Z2_SUB 1024
+
+/* 16-bit uniform -> N(0,1) by quantile table; the 16 outermost cells take 10 more bits from a
+ * dedicated Philox block addressed by (c0,c1,c2,tail_stream).  DESIGN.md "z16". */
+float sqo_z16(const float *zt, uint32_t h, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
+              uint32_t tail_stream) {
+    uint32_t i = h & 0x7FFFu;
+    float z;
+    if (i >= Z_TAIL_FIRST) {
+        uint32_t ctr[4] = {c0, c1, c2, tail_stream}, w[4];
+        sqo_philox4x32_10(ctr, key, w);
+        z = zt[Z1_N + (i - Z_TAIL_FIRST) * Z2_SUB + (w[0] & (Z2_SUB - 1))];
+    } else {
+        z = zt[i];
+    }
+    return (h & 0x8000u) ? -z : z;
+}
+
+static uint32_t halfword(const uint32_t w[4], uint32_t j) { /* j in 0..7 */
+    uint32_t x = w[j >> 1];
+    return (j & 1) ? (x >> 16) : (x & 0xFFFFu);
+}
+
+/* ------------------------------------------------------------------ handle */
+
+typedef struct {
+    int64_t dwell, offset, median; /* Lehmer states: seeds S+2, S+4, S+5 (src/sim.c:238-242) */
+    int64_t *kmer;                 /* one state per k-mer rank, seed S+j (src/sim.c:247-250) */
+} legacy_streams_t;
+
+typedef struct {
+    sqo_config_t cfg;
+    float *mean, *sd_eff; /* level_mean; level_stdv*amp_noise as a FLOAT product (src/sim.c:249) */
+    const float *zt;
+    uint32_t key[2];
+    legacy_streams_t *ls;
+} oracle_t;
+
+void *sqo_open(const sqo_config_t *cfg, const float *model, const float *ztable) {
+    oracle_t *o = (oracle_t *)calloc(1, sizeof(oracle_t));
+    o->cfg = *cfg;
+    uint32_t n = cfg->num_kmer;
+    o->mean = (float *)malloc(sizeof(float) * n);
+    o->sd_eff = (float *)malloc(sizeof(float) * n);
+    for (uint32_t j = 0; j < n; j++) {
+        o->mean[j] = model[2 * j];
+        o->sd_eff[j] = model[2 * j + 1] * cfg->amp_noise;
+    }
+    o->zt = ztable;
+    o->key[0] = (uint32_t)((uint64_t)cfg->seed & 0xFFFFFFFFu);
+    o->key[1] = (uint32_t)((uint64_t)cfg->seed >> 32);
+    if (cfg->rng_mode == SQO_RNG_LEGACY) {
+        int t = cfg->num_thread > 0 ? cfg->num_thread : 1;
+        o->cfg.num_thread = t;
+        o->ls = (legacy_streams_t *)calloc(t, sizeof(legacy_streams_t));
+        int64_t s = cfg->seed; /* src/sim.c:236-257: thread i starts at seed + i*(num_kmer+10) */
+        for (int i = 0; i < t; i++) {
+            o->ls[i].dwell = s + 2;
+            o->ls[i].offset = s + 4;
+            o->ls[i].median = s + 5;
+            o->ls[i].kmer = (int64_t *)malloc(sizeof(int64_t) * n);
+            for (uint32_t j = 0; j < n; j++) o->ls[i].kmer[j] = s + j;
+            s += (int64_t)n + 10;
+        }
+    } else if (!ztable) {
+        free(o->mean); free(o->sd_eff); free(o);
+        return NULL;
+    }
+    return o;
+}
+
+void sqo_close(void *hv) {
+    oracle_t *o = (oracle_t *)hv;
+    if (!o) return;
+    if (o->ls) {
+        for (int i = 0; i < o->cfg.num_thread; i++) free(o->ls[i].kmer);
+        free(o->ls);
+    }
+    free(o->mean);
+    free(o->sd_eff);
+    free(o);
+}
+
+void sqo_free_buf(void *p) { free(p); }
+
+/* ------------------------------------------------------------------ prefix constants */
+/* src/genread.c:37-39 (polyA is 158 x 'A'), :88 (RNA stall), :113 (DNA stall) */
+static const char ADAPTOR_DNA[] = "GGCGTCTGCTTGGGTGTTTAACCTTTTTTTTTTAATGTACTTCGTTCAGTTACGTATTGCT";
+static const char ADAPTOR_RNA[] =
+    "TGATGATGAGGGATAGACGATGGTTGTTTCTGTTGGTGCTGATATTGCTTTTTTTTTTTTTATGATGCAAGATACGCAC";
+static const char STALL_DNA[] = "TTTTTTTTTTTTTTTTTTAATCAA";
+static const char STALL_RNA[] = "AAAAAGAAAAAACCCCCCCCCCCCCCCCCC";
+#define POLYA_LEN 158
+
+/* ------------------------------------------------------------------ the path */
+
+typedef struct {
+    const char *s;
+    int32_t len;
+} seg_t;
+
+/* double -> int16 exactly as the reference's `raw_signal[n] = <double>` store compiles on x86-64
+ * (src/gensig.c:270): truncate toward zero to int32, keep the low 16 bits (no clamp) */
+static int16_t to_i16_d(double v) {
+    int32_t i;
+    if (v >= 2147483648.0) i = INT32_MAX;       /* out-of-int32 inputs never occur for sane */
+    else if (v < -2147483648.0) i = INT32_MIN;  /* profiles; saturate like cvt.rzi.s32.f64   */
+    else i = (int32_t)v;
+    return (int16_t)(uint16_t)((uint32_t)i & 0xFFFFu);
+}
+static int16_t to_i16_f(float v) {
+    int32_t i;
+    if (v >= 2147483648.0f) i = INT32_MAX;
+    else if (v < -2147483648.0f) i = INT32_MIN;
+    else i = (int32_t)v;
+    return (int16_t)(uint16_t)((uint32_t)i & 0xFFFFu);
+}
+
+int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index, int tid, double *offset_out,
+                    double *median_out, int16_t **sig_out, int32_t **ss_out, int64_t *ss_n_out) {
+    oracle_t *o = (oracle_t *)hv;
+    const sqo_config_t *c = &o->cfg;
+    const sqo_profile_t *p = &c->profile;
+    const uint32_t k = c->kmer_size;
+    const int legacy = c->rng_mode == SQO_RNG_LEGACY;
+    const int ideal = (c->flags & SQO_IDEAL) != 0;
+    const int fixed_dwell = ideal || (c->flags & SQO_IDEAL_TIME);
+    const int fixed_amp = ideal || (c->flags & SQO_IDEAL_AMP);
+    const int rna = (c->flags & SQO_RNA) != 0;
+    const int prefix = (c->flags & SQO_PREFIX) != 0;
+    legacy_streams_t *ls = legacy ? &o->ls[tid] : NULL;
+    const uint32_t r_lo = (uint32_t)((uint64_t)read_index & 0xFFFFFFFFu);
+    const uint32_t r_hi = (uint32_t)((uint64_t)read_index >> 32);
+
+    /* --- per-read ADC offset and median_before: src/gensig.c:312-318 --- */
+    double offset, median;
+    if (ideal) {
+        offset = p->offset_mean;
+        median = p->median_before_mean;
+    } else if (legacy) {
+        offset = sqo_lehmer_normal(&ls->offset, p->offset_mean, p->offset_std);
+        median = sqo_lehmer_normal(&ls->median, p->median_before_mean, p->median_before_std);
+    } else {
+        /* one Philox block per read; each deviate mixes two table normals 0.8*z1 + 0.6*z2 so that
+         * per-read values have 2^32 atoms (0.64 + 0.36 = 1 keeps unit variance) */
+        uint32_t ctr[4] = {0, r_lo, r_hi, ST_READ}, w[4];
+        sqo_philox4x32_10(ctr, o->key, w);
+        double z[2];
+        for (int d = 0; d < 2; d++) {
+            float za = sqo_z16(o->zt, w[d] & 0xFFFFu, o->key, 2 * d, r_lo, r_hi, ST_READ_TAIL);
+            float zb = sqo_z16(o->zt, w[d] >> 16, o->key, 2 * d + 1, r_lo, r_hi, ST_READ_TAIL);
+            double a = (double)za * 0.8;
+            double b = (double)zb * 0.6;
+            z[d] = a + b;
+        }
+        double t0 = z[0] * p->offset_std;
+        offset = t0 + p->offset_mean;
+        double t1 = z[1] * p->median_before_std;
+        median = t1 + p->median_before_mean;
+    }
+    *offset_out = offset;
+    *median_out = median;
+
+    /* --- sequence segments: src/genread.c:95-123 (attach_prefix) + :88-89 (RNA stall) --- */
+    char *joined = NULL;
+    seg_t seg[2];
+    int nseg = 1;
+    if (prefix) {
+        if (rna) {
+            int32_t al = (int32_t)strlen(ADAPTOR_RNA);
+            joined = (char *)malloc((size_t)len + POLYA_LEN + al + 1);
+            memcpy(joined, read, (size_t)len);
+            memset(joined + len, 'A', POLYA_LEN);
+            memcpy(joined + len + POLYA_LEN, ADAPTOR_RNA, (size_t)al);
+            len += POLYA_LEN + al;
+            seg[1].s = STALL_RNA;
+            seg[1].len = (int32_t)strlen(STALL_RNA);
+            nseg = 2;
+        } else {
+            int32_t sl = (int32_t)strlen(STALL_DNA), al = (int32_t)strlen(ADAPTOR_DNA);
+            joined = (char *)malloc((size_t)len + sl + al + 1);
+            memcpy(joined, STALL_DNA, (size_t)sl);
+            memcpy(joined + sl, ADAPTOR_DNA, (size_t)al);
+            memcpy(joined + sl + al, read, (size_t)len);
+            len += sl + al;
+        }
+        joined[len] = '\0';
+        read = joined;
+    }
+    seg[0].s = read;
+    seg[0].len = len;
+
+    /* --- k-mer list (rank per k-mer), src/gensig.c:240-253 --- */
+    int64_t nk_seg[2] = {0, 0}, nk = 0;
+    for (int g = 0; g < nseg; g++) {
+        nk_seg[g] = seg[g].len < (int32_t)k ? 5 : (int64_t)seg[g].len - k + 1; /* :242-245 "a hack" */
+        nk += nk_seg[g];
+    }
+    uint32_t *rank = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nk);
+    int32_t *sps = (int32_t *)malloc(sizeof(int32_t) * (size_t)nk);
+    {
+        int64_t q = 0;
+        for (int g = 0; g < nseg; g++) {
+            /* short read: 5 k-mers of "ACGTACGTACGT"; for k=9 the last window runs onto the
+             * terminating NUL, which ranks 0 like any unknown base */
+            static const char HACK[16] = "ACGTACGTACGT\0\0\0";
+            const char *s = seg[g].len < (int32_t)k ? HACK : seg[g].s;
+            for (int64_t i = 0; i < nk_seg[g]; i++, q++)
+                rank[q] = c->meth ? sqo_meth_kmer_rank(s + i, k) : sqo_kmer_rank(s + i, k);
+        }
+    }
+
+    /* --- dwell per k-mer, src/gensig.c:254-257 --- */
+    int64_t total = 0;
+    for (int64_t i = 0; i < nk; i++) {
+        int d = (int)p->dwell_mean;
+        if (!fixed_dwell) {
+            double x;
+            if (legacy) {
+                x = sqo_lehmer_normal(&ls->dwell, p->dwell_mean, p->dwell_std);
+            } else {
+                uint32_t ctr[4] = {(uint32_t)(i >> 3), r_lo, r_hi, ST_DWELL}, w[4];
+                sqo_philox4x32_10(ctr, o->key, w);
+                float z = sqo_z16(o->zt, halfword(w, (uint32_t)(i & 7)), o->key, (uint32_t)i, r_lo, r_hi,
+                                  ST_DWELL_TAIL);
+                double t = (double)z * p->dwell_std;
+                x = t + p->dwell_mean;
+            }
+            d = (int)round(x);
+            if (d < 1) d = -d + 1;
+        }
+        sps[i] = d;
+        total += d;
+    }
+    /* NB legacy mode: the reference draws a k-mer's dwell immediately before that k-mer's samples,
+     * but the dwell stream is a separate state from every per-k-mer stream (k-mer 2 shares its SEED
+     * with it, src/sim.c:240,249, not its state), so drawing all dwells first is exact. */
+
+    /* --- samples, src/gensig.c:259-272 --- */
+    int16_t *raw = (int16_t *)malloc(sizeof(int16_t) * (size_t)(total > 0 ? total : 1));
+    const double scale = p->digitisation / p->range; /* Philox mode only */
+    int64_t n = 0;
+    for (int64_t i = 0; i < nk; i++) {
+        const uint32_t r = rank[i];
+        const float mean = o->mean[r];
+        if (fixed_amp) {
+            int16_t v = to_i16_d((double)mean * p->digitisation / p->range - offset);
+            for (int j = 0; j < sps[i]; j++) raw[n++] = v;
+        } else if (legacy) {
+            for (int j = 0; j < sps[i]; j++) {
+                float s = (float)sqo_lehmer_normal(&ls->kmer[r], (double)mean, (double)o->sd_eff[r]);
+                raw[n++] = to_i16_d((double)s * p->digitisation / p->range - offset);
+            }
+        } else {
+            double a = (double)o->sd_eff[r] * scale;
+            double b0 = (double)mean * scale;
+            double b = b0 - offset;
+            const float A = (float)a, B = (float)b;
+            for (int j = 0; j < sps[i]; j++, n++) {
+                /* Philox draws are addressed by the position in the EMITTED signal (after the RNA
+                 * reversal of src/gensig.c:348-354), eight 16-bit draws per block */
+                uint32_t q = (uint32_t)(rna ? total - 1 - n : n);
+                uint32_t ctr[4] = {q >> 3, r_lo, r_hi, ST_AMP}, w[4];
+                sqo_philox4x32_10(ctr, o->key, w);
+                float z = sqo_z16(o->zt, halfword(w, q & 7), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
+                raw[n] = to_i16_f(fmaf(z, A, B));
+            }
+        }
+    }
+
+    /* --- RNA adaptor level shift, src/genread.c:80-86 (stall k-mers were generated above as
+     * segment 1, which is what the 2nd gen_sig_core_seq call at :89 appends) --- */
+    if (prefix && rna) {
+        int64_t n0 = 0;
+        for (int64_t i = 0; i < nk_seg[0]; i++) n0 += sps[i];
+        int64_t st = n0 - (int64_t)strlen(ADAPTOR_RNA) * (int)p->dwell_mean;
+        if (st < 0) st = 0; /* the reference would write out of bounds here */
+        int16_t off = (int16_t)(30 * p->digitisation / p->range);
+        for (int64_t i = st; i < n0; i++) raw[i] = (int16_t)(raw[i] - off);
+    }
+
+    /* --- RNA: 3'->5' emission, src/gensig.c:348-354 --- */
+    if (rna) {
+        for (int64_t i = 0; i < total / 2; i++) {
+            int16_t t = raw[i];
+            raw[i] = raw[total - 1 - i];
+            raw[total - 1 - i] = t;
+        }
+    }
+
+    *sig_out = raw;
+    if (ss_out) {
+        *ss_out = sps; /* aln->ss, src/gensig.c:273-281 */
+        *ss_n_out = nk;
+    } else {
+        free(sps);
+    }
+    free(rank);
+    free(joined);
+    return total;
+}

@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""Generate the standard-normal quantile tables used by the Philox path (DESIGN.md "z16").
+
+The Philox path turns one 16-bit uniform h into a standard normal deviate by table lookup:
+
+    sign = h >> 15,  i = h & 0x7FFF
+    cell i of the half-normal = [a_i, b_i),  a_i = ndtri(0.5 + i/65536),  b_i = ndtri(0.5 + (i+1)/65536)
+    z = +-Z1[i],  Z1[i] = sqrt(E[z^2 | a_i <= z < b_i])          (the cell's conditional RMS)
+
+so every cell has probability 2^-16 and the discrete law has mean 0 and variance EXACTLY 1
+(sum_i 2^-15 * Z1[i]^2 = E[z^2] = 1).  The 16 outermost cells (i >= 32752, z > 3.49 sigma,
+probability 2^-11) are refined once more with 10 fresh bits: sub-cell j of tail cell t=i-32752 is
+[ndtri(0.5 + (i + j/1024)/65536), ndtri(0.5 + (i + (j+1)/1024)/65536)) with representative
+Z2[t*1024+j] = conditional RMS again, which keeps the variance exact and extends the support to
+~5.8 sigma (the reference's Box-Muller on a 31-bit Lehmer uniform reaches 6.55 sigma,
+/root/reference src/rand.h:79-94).
+
+Output: squigulator_b200/data/ztable_v1.bin = float32 LE, Z1 (32768) followed by Z2 (16384).
+The file is data shared by the product (embedded into libsqg.so) and by the oracle (loaded at run
+time); tests/test_ztable.py re-derives it independently with mpmath.
+"""
+import os
+import sys
+
+import numpy as np
+from scipy.special import ndtri, ndtr
+
+N1 = 32768
+TAIL_CELLS = 16
+SUB = 1024
+
+
+def cond_rms(a, b):
+    """sqrt(E[z^2 | a<=z<b]) for finite cells, 16-point Gauss-Legendre per cell (no cancellation)."""
+    x, w = np.polynomial.legendre.leggauss(16)
+    mid = 0.5 * (a + b)[:, None]
+    half = 0.5 * (b - a)[:, None]
+    z = mid + half * x[None, :]
+    pdf = np.exp(-0.5 * z * z)
+    num = (w[None, :] * z * z * pdf).sum(axis=1)
+    den = (w[None, :] * pdf).sum(axis=1)
+    return np.sqrt(num / den)
+
+
+def cond_rms_inf(a):
+    """sqrt(E[z^2 | z>=a]) = sqrt(1 + a*phi(a)/Q(a))"""
+    phi = np.exp(-0.5 * a * a) / np.sqrt(2 * np.pi)
+    q = ndtr(-a)
+    return np.sqrt(1.0 + a * phi / q)
+
+
+def build():
+    e1 = ndtri(0.5 + np.arange(N1 + 1, dtype=np.float64) / 65536.0)  # e1[N1] = ndtri(1.0) = inf
+    z1 = np.empty(N1, dtype=np.float64)
+    z1[:-1] = cond_rms(e1[:-2], e1[1:-1])
+    z1[-1] = cond_rms_inf(e1[-2])
+
+    z2 = np.empty(TAIL_CELLS * SUB, dtype=np.float64)
+    first = N1 - TAIL_CELLS
+    for t in range(TAIL_CELLS):
+        i = first + t
+        # upper-tail probability of sub-cell edges, computed as 0.5 - (i + j/SUB)/65536 exactly in binary
+        q = 0.5 - (i + np.arange(SUB + 1, dtype=np.float64) / SUB) / 65536.0
+        with np.errstate(divide="ignore"):
+            e = -ndtri(q)  # q[-1] == 0 for the last cell -> +inf
+        zz = np.empty(SUB, dtype=np.float64)
+        if np.isinf(e[-1]):
+            zz[:-1] = cond_rms(e[:-2], e[1:-1])
+            zz[-1] = cond_rms_inf(e[-2])
+        else:
+            zz[:] = cond_rms(e[:-1], e[1:])
+        z2[t * SUB:(t + 1) * SUB] = zz
+    return z1.astype(np.float32), z2.astype(np.float32)
+
+
+def main():
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
+        os.path.dirname(os.path.abspath(__file__)), "..", "squigulator_b200", "data", "ztable_v1.bin")
+    z1, z2 = build()
+    assert np.all(np.diff(z1) > 0) and np.all(np.diff(z2) > 0)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "wb") as f:
+        f.write(z1.astype("<f4").tobytes())
+        f.write(z2.astype("<f4").tobytes())
+    v1 = (z1.astype(np.float64) ** 2).mean()
+    # exact variance of the two-level law: body cells + refined tail cells
+    body = (z1[:N1 - TAIL_CELLS].astype(np.float64) ** 2).sum() / N1
+    tail = (z2.astype(np.float64) ** 2).sum() / (N1 * SUB)
+    print(f"wrote {out}: Z1[0]={z1[0]:.3e} Z1[-1]={z1[-1]:.4f} Z2[-1]={z2[-1]:.4f} "
+          f"var(level1)={v1:.9f} var(two-level)={body + tail:.9f}")
+
+
+if __name__ == "__main__":
+    main()
