@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""bench.py — int16 raw samples/s of the signal-generation hot path on N B200s (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libsqg.so)
+    python bench.py --impl reference --gpus N ...             # the reference's own CPU gen_sig on host cores
+
+A step = one pass of the whole hot path (dwell pass, scans, signal kernel) over one resident batch of
+synthetic reads; `value` has inputs and outputs resident in HBM, `e2e` goes through the host-buffer
+C-ABI call (sqg_submit/sqg_wait) with the H2D/D2H copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2] (per-GPU shard; the north_star target is quoted on this profile)
+    "dna-r10-prom": dict(profile="dna-r10-prom", k=9, rna=False, config="configs[2]"),
+    # configs[1]
+    "dna-r9-prom": dict(profile="dna-r9-prom", k=6, rna=False, config="configs[1]"),
+    # configs[3] shape: whole transcripts, ragged, reversed output, fixed dwell 31
+    "rna004-prom": dict(profile="rna004-prom", k=9, rna=True, config="configs[3]"),
+}
+
+
+def synth_model(num_kmer, seed=7):
+    """random-init pore model of the right shape (level_mean ~ U(60,130) pA, level_stdv ~ U(1,4) pA)"""
+    rs = np.random.RandomState(seed)
+    m = np.empty(2 * num_kmer, dtype=np.float32)
+    m[0::2] = rs.uniform(60, 130, num_kmer)
+    m[1::2] = rs.uniform(1.0, 4.0, num_kmer)
+    return m
+
+
+def synth_reads(n_reads, mean_len, rna, seed, genome_mb=64):
+    """Reads as the reference's sampler would cut them from a synthetic i.i.d. ACGT genome: length ~
+    Gamma(2, rlen/2) (src/sim.c:243), uniform position, clipped at the contig end, <200 nt rejected
+    (src/genread.c:125-154), strand coin + reverse complement.  RNA: whole 'transcripts' of ragged length
+    (283..6943 nt like the sequins, mean ~1355)."""
+    rs = np.random.RandomState(seed)
+    g = rs.randint(0, 4, genome_mb << 20).astype(np.uint8)
+    comp = np.array([3, 2, 1, 0], dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    if rna:
+        lens = np.clip(rs.gamma(2.2, 1355 / 2.2, n_reads), 283, 6943).astype(np.int64)
+    else:
+        lens = rs.gamma(2.0, mean_len / 2.0, int(n_reads * 1.1) + 16).astype(np.int64)
+        lens = lens[lens >= 200][:n_reads]
+    pos = (rs.random_sample(len(lens)) * (len(g) - 1)).astype(np.int64)
+    lens = np.minimum(lens, len(g) - pos)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    bases = np.empty(off[-1], dtype=np.uint8)
+    strand = rs.randint(0, 2, len(lens))
+    for i in range(len(lens)):
+        s = g[pos[i]:pos[i] + lens[i]]
+        if not rna and strand[i]:
+            s = comp[s[::-1]]
+        bases[off[i]:off[i + 1]] = lut[s]
+    return bases, off
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (NVML, 20 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.power = index, False, [], set(), None, []
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+                "reasons": sorted(self.reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own gen_sig (oracle/_ref/libsqref.so, built from /root/reference unmodified), else
+# the plain-C oracle port.  The only place bench.py executes anything under oracle/.
+def cpu_reference_run(wl, bases, off, seed, max_threads=None):
+    from tests import helpers as H
+    prof, flags = H.PRESETS[wl["profile"]]
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, max_threads or cores)
+    n_reads = len(off) - 1
+    so = os.path.join(ROOT, "oracle", "_ref", "libsqref.so")
+    if os.path.exists(so):
+        lib = C.CDLL(so)
+        lib.sqref_open.restype = C.c_void_p
+        lib.sqref_open.argtypes = [C.POINTER(H.Profile), C.c_uint32, C.c_int64, C.c_int32, C.c_float, C.c_int,
+                                   C.c_char_p, C.c_char_p, C.c_int]
+        lib.sqref_run_batch.restype = C.c_int64
+        lib.sqref_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        lib.sqref_close.argtypes = [C.c_void_p]
+        p = H.make_profile(prof)
+        h = lib.sqref_open(C.byref(p), flags, seed, nthreads, 1.0, 0, None, None, 0)  # built-in tables of the reference
+        lens = np.ascontiguousarray(np.diff(off).astype(np.int32))
+        t0 = time.perf_counter()
+        total = lib.sqref_run_batch(h, bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                    lens.ctypes.data_as(C.c_void_p), n_reads, nthreads)
+        dt = time.perf_counter() - t0
+        lib.sqref_close(h)
+        return dict(kind="reference", cores=nthreads, samples=int(total), seconds=dt)
+    # port: single-threaded oracle, legacy (reference-exact) RNG
+    o = H.Oracle(H.load_oracle(), prof, flags, wl["k"], 4 ** wl["k"], synth_model(4 ** wl["k"]), seed, H.RNG_LEGACY)
+    raw = bases.tobytes()
+    t0 = time.perf_counter()
+    total = 0
+    for i in range(n_reads):
+        total += len(o.gen_sig(raw[off[i]:off[i + 1]], read_index=i)["sig"])
+    dt = time.perf_counter() - t0
+    o.close()
+    return dict(kind="port", cores=1, samples=total, seconds=dt)
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    reads_per_step = args.cpu_reads if args.cpu_reads else max(cores * 40, 64)
+    bases, off = synth_reads(reads_per_step, args.read_len, wl["rna"], seed=1234)
+    times, samples = [], 0
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(wl, bases, off, seed=1)
+        if i >= args.warmup:
+            times.append(r["seconds"])
+            samples += r["samples"]
+    v = samples / sum(times)
+    dm = dict(__import__("tests.helpers", fromlist=["PRESETS"]).PRESETS[wl["profile"]][0])["dwell_mean"]
+    sample = f"{reads_per_step} reads (~{r['samples']} samples) per step, gen_sig only (no SLOW5 encode), {r['cores']} threads"
+    line = {"impl": "reference", "metric": "int16_raw_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gbases_per_s": v / dm / 1e9,
+            "config": {"workload": f"{wl['config']}: -x {wl['profile']}, reads cut from a synthetic iid genome, mean length {args.read_len}",
+                       "reads_per_step": reads_per_step},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, steps, warmup, with_e2e=True):
+    import torch
+    from squigulator_b200.api import PROFILES
+    prof = PROFILES[wl["profile"]][0]
+    bases, off = synth_reads(reads_per_step, args.read_len, wl["rna"], seed=1000 + rank)
+    n_reads = len(off) - 1
+    first = rank * n_reads  # read-index range of this GPU: the Philox counter makes the job independent of N
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- kernel-only: resident batch ----
+    db = gen.dev_batch(bases, off, first_read_index=first)
+    gen.dev_batch_run(db, max(warmup, 3))
+    info = gen.dev_batch_info(db)
+    sampler = ClockSampler(device)
+    l0 = gen.launch_count()
+    barrier()
+    sampler.start()
+    w0 = time.perf_counter()
+    ms_total, ms_k4 = gen.dev_batch_run(db, steps)
+    barrier()
+    wall = time.perf_counter() - w0
+    sampler.stop_flag = True
+    sampler.join()
+    launches = gen.launch_count() - l0
+    ms = max_over_ranks(ms_total)
+    samples_all = sum_over_ranks(float(info["samples"]))
+    out.update(value=samples_all * steps / (ms * 1e-3), ms_per_step=ms / steps, wall_s=wall, clocks=sampler.summary(),
+               gpu_launches=int(launches), samples_per_step_per_gpu=info["samples"], kmers_per_step_per_gpu=info["kmers"],
+               reads_per_step_per_gpu=n_reads)
+    # roofline of the signal kernel on this rank: algorithmic bytes = 2 B/sample + 1 B per k-mer (one base)
+    peak, how = measured_peak()
+    alg_bytes = 2.0 * info["samples"] + 1.0 * info["kmers"]
+    k4_ms = ms_k4 / steps
+    out["roofline"] = {"bound": "hbm", "kernel": "signal_kernel", "achieved": alg_bytes / (k4_ms * 1e-3) / 1e9, "peak": peak,
+                       "unit": "GB/s", "frac": alg_bytes / (k4_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                       "peak_source": how, "kernel_ms": k4_ms, "kernel_share_of_step": ms_k4 / ms_total,
+                       "algorithmic_bytes_per_launch": alg_bytes}
+    gen.dev_batch_destroy(db)
+
+    # ---- end to end: host buffers through the asynchronous C-ABI (H2D + kernels + D2H every step) ----
+    if with_e2e:
+        e_reads = min(n_reads, args.e2e_reads)
+        e_off = np.ascontiguousarray(off[:e_reads + 1])
+        nb = int(e_off[-1])
+        lib = sq.load_library()
+        hp = lib.sqg_host_alloc(nb)  # pinned input buffer
+        hb = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nb,))
+        hb[:] = bases[:nb]
+        e_steps = max(6, min(steps, 24))
+        checks = 0
+
+        def pipeline(n):
+            nonlocal checks
+            inflight, tot, d2h = [], 0, 0
+            for i in range(n):
+                inflight.append(gen.submit(hb, e_off, first_read_index=first))
+                if len(inflight) == 3:
+                    t = inflight.pop(0)
+                    r = gen.wait(t)
+                    tot += r.total_samples
+                    d2h = int(r.sig_off[r.n_reads - 1] + ((r.len_raw_signal[r.n_reads - 1] + 63) & ~63)) * 2 + r.n_reads * 28
+                    checks ^= int(r.signal[0])  # touch the result on the host
+                    gen.release(t)
+            for t in inflight:
+                r = gen.wait(t)
+                tot += r.total_samples
+                gen.release(t)
+            return tot, d2h
+
+        pipeline(3)
+        barrier()
+        t0 = time.perf_counter()
+        tot, d2h = pipeline(e_steps)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out["e2e"] = {"value": sum_over_ranks(float(tot)) / dt, "unit": "samples/s",
+                      "h2d_bytes_per_step": nb + (e_reads * 64), "d2h_bytes_per_step": d2h,
+                      "steps": e_steps, "reads_per_step_per_gpu": e_reads, "slots": 3,
+                      "api": "sqg_submit/sqg_wait/sqg_release (pinned host bases in, pinned host int16 out)"}
+        lib.sqg_host_free(hp)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dna-r10-prom", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads-per-step", type=int, default=32768, help="reads in the resident batch of each GPU")
+    ap.add_argument("--e2e-reads", type=int, default=4096)
+    ap.add_argument("--read-len", type=int, default=10000)
+    ap.add_argument("--cpu-reads", type=int, default=0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the CPU baseline")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import squigulator_b200 as sq
+    from squigulator_b200.api import PROFILES
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in squigulator_b200)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    def make_gen(w):
+        # pore-model table: created on rank 0, broadcast once over NCCL, handed to the library as a device pointer
+        n = 4 ** w["k"]
+        t = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{local}")
+        if rank == 0:
+            t.copy_(torch.from_numpy(synth_model(n)))
+        if world > 1:
+            dist.broadcast(t, src=0)
+        torch.cuda.synchronize()
+        prof, flags = PROFILES[w["profile"]]
+        return sq.SignalGenerator(dict(prof), None, w["k"], flags=flags, seed=1, device=local, n_slots=3,
+                                  device_model_ptr=t.data_ptr()), t
+
+    gen, _keep = make_gen(wl)
+    res = measure_gpu(args, wl, gen, sq, dist, rank, world, local, args.reads_per_step, args.steps, args.warmup)
+    # HBM write ceiling (store-only kernel over 8 GiB) for context
+    store_ms = gen.bench_store(8 << 30, 5)
+    store_ms = gen.bench_store(8 << 30, 10)
+    res["store_only_gbs"] = (8 << 30) * 10 / (store_ms * 1e-3) / 1e9
+    gen.close()
+
+    extra = {}
+    if not args.no_extra:
+        for name in sorted(WORKLOADS):
+            if name == args.workload:
+                continue
+            w2 = WORKLOADS[name]
+            g2, _k2 = make_gen(w2)
+            rps = args.reads_per_step if not w2["rna"] else args.reads_per_step * 4
+            r2 = measure_gpu(args, w2, g2, sq, dist, rank, world, local, rps, max(10, args.steps // 2), 3, with_e2e=False)
+            g2.close()
+            extra[name] = {"config": w2["config"], "value": r2["value"], "ms_per_step": r2["ms_per_step"],
+                           "roofline_frac": r2["roofline"]["frac"], "kernel_ms": r2["roofline"]["kernel_ms"],
+                           "samples_per_step_per_gpu": r2["samples_per_step_per_gpu"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        cores = os.cpu_count() or 1
+        n_cpu = args.cpu_reads if args.cpu_reads else max(cores * 40, 64)
+        cb, co = synth_reads(n_cpu, args.read_len, wl["rna"], seed=1234)
+        r = cpu_reference_run(wl, cb, co, seed=1)
+        cpu = {"value": r["samples"] / r["seconds"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{n_cpu} reads of the same workload ({r['samples']} samples, {r['seconds']:.1f} s), gen_sig only, {r['cores']} host threads"}
+
+    if rank == 0:
+        prof = PROFILES[wl["profile"]][0]
+        line = {"metric": "int16_raw_samples_per_s", "value": res["value"], "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "gbases_per_s": res["value"] / prof["dwell_mean"] / 1e9,
+                "config": {"workload": f"{wl['config']} per-GPU shard: -x {wl['profile']}, reads cut (gamma length, mean {args.read_len}) "
+                                       f"from a synthetic iid ACGT genome, random-init {wl['k']}-mer table; step = one resident batch",
+                           "reads_per_step_per_gpu": res["reads_per_step_per_gpu"],
+                           "samples_per_step_per_gpu": res["samples_per_step_per_gpu"],
+                           "l2": "output per step (GBs) far exceeds the 126 MB L2; no flush needed",
+                           "rng": "philox4x32-10", "parallelism": f"reads sharded over {world} GPU(s), no hot-path collective"},
+                "clocks": res["clocks"], "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"],
+                "roofline": res["roofline"], "cpu_baseline": cpu, "store_only_gbs": res["store_only_gbs"],
+                "wall_s_timed_region": res["wall_s"], "other_workloads": extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

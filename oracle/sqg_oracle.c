@@ -321,9 +321,12 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
             if (legacy) {
                 x = sqo_lehmer_normal(&ls->dwell, p->dwell_mean, p->dwell_std);
             } else {
-                uint32_t ctr[4] = {(uint32_t)(i >> 3), r_lo, r_hi, ST_DWELL}, w[4];
+                /* draw index: position in the read's k-mer list; a 2nd segment (RNA stall) starts at
+                 * the next multiple of 8 so that every block of 8 draws lies inside one segment */
+                int64_t di = i < nk_seg[0] ? i : ((nk_seg[0] + 7) & ~(int64_t)7) + (i - nk_seg[0]);
+                uint32_t ctr[4] = {(uint32_t)(di >> 3), r_lo, r_hi, ST_DWELL}, w[4];
                 sqo_philox4x32_10(ctr, o->key, w);
-                float z = sqo_z16(o->zt, halfword(w, (uint32_t)(i & 7)), o->key, (uint32_t)i, r_lo, r_hi,
+                float z = sqo_z16(o->zt, halfword(w, (uint32_t)(di & 7)), o->key, (uint32_t)di, r_lo, r_hi,
                                   ST_DWELL_TAIL);
                 double t = (double)z * p->dwell_std;
                 x = t + p->dwell_mean;

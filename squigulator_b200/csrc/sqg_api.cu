@@ -1,0 +1,834 @@
+// sqg_api.cu — C ABI (include/sqg.h) over the kernels in sqg_kernels.cuh.
+//
+// Host side of the drop-in: what the reference does per batch in process_db()/work_db()
+// (src/sim.c:622, src/thread.c:119) around gen_sig() is done here per SLOT: a CUDA stream with its own
+// device buffers and pinned staging.  sqg_submit hands batches to slot worker threads, so the H2D
+// copy, the kernels and the D2H copy of consecutive batches overlap each other and the caller's
+// host-side record encoding.
+//
+// There is deliberately NO CPU implementation in this library: without a CUDA device every entry point
+// fails with SQG_ERR_NODEVICE.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sqg.h"
+#include "sqg_kernels.cuh"
+
+extern "C" const float sqg_ztable_blob[];  // Z1 ++ Z2, embedded from data/ztable_v1.bin (ztable_blob.S)
+
+namespace {
+
+using namespace sqg;
+
+thread_local std::string g_init_error;
+
+// constant sequences of --prefix (src/genread.c:37-39, :88, :113) and of the short-read rule
+// (src/gensig.c:242-245), kept in front of every uploaded base buffer
+constexpr int CONST_REGION = 512;
+constexpr int C_HACK = 0, C_DNA_PREFIX = 32, C_RNA_SUFFIX = 128, C_RNA_STALL = 384;
+const char STALL_DNA[] = "TTTTTTTTTTTTTTTTTTAATCAA";
+const char ADAPTOR_DNA[] = "GGCGTCTGCTTGGGTGTTTAACCTTTTTTTTTTAATGTACTTCGTTCAGTTACGTATTGCT";
+const char ADAPTOR_RNA[] = "TGATGATGAGGGATAGACGATGGTTGTTTCTGTTGGTGCTGATATTGCTTTTTTTTTTTTTATGATGCAAGATACGCAC";
+const char STALL_RNA[] = "AAAAAGAAAAAACCCCCCCCCCCCCCCCCC";
+constexpr int POLYA_LEN = 158;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (p) {
+            cudaStreamSynchronize(st);
+            cudaFree(p);
+        }
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 2);
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, ncap * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// One in-flight batch: stream + device buffers + pinned host staging/result buffers
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> kev;  // per-step event pairs around the signal kernel
+    DevBuf<uint8_t> d_bases;
+    DevBuf<SegDesc> d_segs;
+    DevBuf<ReadDesc> d_reads;
+    DevBuf<int32_t> d_tile_seg;
+    DevBuf<uint32_t> d_tile_sum, d_tile_base, d_siglen, d_n0;
+    DevBuf<int64_t> d_sigoff, d_meta;
+    DevBuf<double> d_offset, d_median;
+    DevBuf<int16_t> d_sig;
+    DevBuf<int32_t> d_ss;
+    PinBuf<SegDesc> h_segs;
+    PinBuf<ReadDesc> h_reads;
+    PinBuf<int64_t> h_meta, h_sigoff, h_len64, h_ss_off;
+    PinBuf<uint32_t> h_siglen;
+    PinBuf<double> h_offset, h_median;
+    PinBuf<int16_t> h_sig;
+    PinBuf<int32_t> h_ss;
+    // batch geometry
+    int64_t n_reads = 0, n_segs = 0, n_tiles = 0, total_kmers = 0, total_bases = 0, first_read = 0;
+    uint32_t want = 0;
+    int64_t arena_need = 0, total_samples = 0;
+    bool const_written = false;
+    void release() {
+        d_bases.release(); d_segs.release(); d_reads.release(); d_tile_seg.release(); d_tile_sum.release();
+        d_tile_base.release(); d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
+        d_offset.release(); d_median.release(); d_sig.release(); d_ss.release();
+        h_segs.release(); h_reads.release(); h_meta.release(); h_sigoff.release(); h_len64.release();
+        h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
+        h_ss.release();
+        for (auto e : kev) cudaEventDestroy(e);
+        kev.clear();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr; ev0 = ev1 = nullptr;
+    }
+};
+
+struct Job {
+    sqg_ticket_t ticket;
+    int slot;
+    int64_t n_reads;
+    const char *bases;
+    const int64_t *base_off;
+    int64_t first_read;
+    uint32_t want;
+    int status = 1;  // 1 = running, <=0 = done with that code
+};
+
+}  // namespace
+
+struct sqg_dev_batch {
+    Slot slot;
+    bool planned = false;
+};
+
+struct sqg_ctx {
+    sqg_config_t cfg;
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+    DevBuf<float2> d_model;
+    DevBuf<float> d_z;  // Z1 ++ Z2
+    GenParams base;     // configuration-derived part of the kernel parameters
+    bool noisy = false, rand_dwell = false, meth = false, rev = false, prefix = false;
+    int model_in_smem = 0;
+    size_t k4_smem = 0;
+    int k4_grid_per_sm = 1;
+    std::atomic<int64_t> launches{0};
+    Slot sync_slot;  // used by sqg_gen_batch / sqg_gen_sig
+    // dispatcher
+    std::vector<Slot> slots;
+    std::vector<std::thread> workers;
+    std::vector<std::deque<Job *>> queues;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::map<sqg_ticket_t, Job *> jobs;
+    std::vector<int> slot_busy;
+    sqg_ticket_t next_ticket = 1;
+    bool stopping = false;
+};
+
+namespace {
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char b__[512];                                                                           \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->err = b__;                                                                          \
+            return e__ == cudaErrorMemoryAllocation ? SQG_ERR_NOMEM : SQG_ERR_CUDA;                  \
+        }                                                                                            \
+    } while (0)
+
+int fail(sqg_ctx *ctx, int code, const char *msg) {
+    if (ctx) ctx->err = msg; else g_init_error = msg;
+    return code;
+}
+
+typedef void (*k4_fn)(const GenParams);
+
+k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev) {
+#define K4(a, b, c, d) (k4_fn) signal_kernel<a, b, c, d>
+    static const k4_fn tab[16] = {
+        K4(false, false, false, false), K4(false, false, false, true), K4(false, false, true, false), K4(false, false, true, true),
+        K4(false, true, false, false),  K4(false, true, false, true),  K4(false, true, true, false),  K4(false, true, true, true),
+        K4(true, false, false, false),  K4(true, false, false, true),  K4(true, false, true, false),  K4(true, false, true, true),
+        K4(true, true, false, false),   K4(true, true, false, true),   K4(true, true, true, false),   K4(true, true, true, true)};
+#undef K4
+    return tab[(noisy << 3) | (rnd << 2) | (meth << 1) | (int)rev];
+}
+
+int slot_init(sqg_ctx *ctx, Slot &s) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s.ev0));
+    CU(cudaEventCreate(&s.ev1));
+    return SQG_OK;
+}
+
+// ---- host-side batch preparation: reads -> segments -> tiles (replaces the per-read bookkeeping at the
+// top of gen_sig_core / gen_sig_core_seq, src/gensig.c:240-245, :302-309, and attach_prefix) ----
+int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, const int64_t *base_off,
+                 int64_t first_read, uint32_t want) {
+    if (n_reads < 0 || (n_reads > 0 && (!bases || !base_off))) return fail(ctx, SQG_ERR_ARG, "null input");
+    if (n_reads > 0x3FFFFFFF) return fail(ctx, SQG_ERR_ARG, "too many reads in one batch");
+    const int k = (int)ctx->cfg.kmer_size;
+    const int T = ctx->base.T;
+    const bool prefix = ctx->prefix, rna = ctx->rev;
+    const int64_t nseg_max = n_reads * (prefix && rna ? 2 : 1);
+    CU(s.h_segs.ensure((size_t)std::max<int64_t>(nseg_max, 1)));
+    CU(s.h_reads.ensure((size_t)std::max<int64_t>(n_reads, 1)));
+    CU(s.h_ss_off.ensure((size_t)n_reads + 1));
+    const int64_t user0 = base_off ? base_off[0] : 0;
+    const int64_t total_bases = n_reads ? base_off[n_reads] - user0 : 0;
+    int64_t nseg = 0, ntile = 0, nk_total = 0;
+    const int dna_prefix_len = (int)(strlen(STALL_DNA) + strlen(ADAPTOR_DNA));
+    const int rna_suffix_len = POLYA_LEN + (int)strlen(ADAPTOR_RNA);
+    const int stall_rna_len = (int)strlen(STALL_RNA);
+    for (int64_t r = 0; r < n_reads; r++) {
+        const int64_t len64 = base_off[r + 1] - base_off[r];
+        if (len64 < 0 || len64 > 0x7FFFFFF0) return fail(ctx, SQG_ERR_ARG, "read length out of range (int32, as in the reference)");
+        const int len = (int)len64;
+        const int64_t uoff = CONST_REGION + (base_off[r] - user0);
+        ReadDesc &rd = s.h_reads.p[r];
+        rd.seg0 = (int32_t)nseg;
+        rd.nseg = 1;
+        rd.ss_off = nk_total;
+        rd.shift_len = 0;
+        rd.pad = 0;
+        s.h_ss_off.p[r] = nk_total;
+        SegDesc &sg = s.h_segs.p[nseg];
+        int full_len;
+        if (prefix && !rna) {  // stall + adaptor in front (src/genread.c:112-121)
+            sg.off_a = C_DNA_PREFIX; sg.len_a = dna_prefix_len; sg.off_b = uoff;
+            full_len = dna_prefix_len + len;
+        } else if (prefix && rna) {  // polyA + adaptor behind (src/genread.c:99-110)
+            sg.off_a = uoff; sg.len_a = len; sg.off_b = C_RNA_SUFFIX;
+            full_len = len + rna_suffix_len;
+        } else {
+            sg.off_a = uoff; sg.len_a = len; sg.off_b = uoff;
+            full_len = len;
+        }
+        if (full_len < k) {  // src/gensig.c:242-245: 5 k-mers of "ACGTACGTACGT"
+            sg.off_a = C_HACK; sg.len_a = 16; sg.off_b = C_HACK;
+            sg.nk = 5;
+        } else {
+            sg.nk = full_len - k + 1;
+        }
+        sg.read = (int32_t)r;
+        sg.k0 = 0;
+        sg.k0_rng = 0;
+        sg.tile0 = (int32_t)ntile;
+        ntile += (sg.nk + T - 1) / T;
+        nk_total += sg.nk;
+        nseg++;
+        if (prefix && rna) {  // the stall appended by gen_prefix_rna (src/genread.c:88-89)
+            const int nk0 = sg.nk;
+            SegDesc &s2 = s.h_segs.p[nseg];
+            s2.off_a = C_RNA_STALL; s2.len_a = stall_rna_len; s2.off_b = C_RNA_STALL;
+            s2.nk = stall_rna_len < k ? 5 : stall_rna_len - k + 1;
+            if (stall_rna_len < k) { s2.off_a = C_HACK; s2.len_a = 16; s2.off_b = C_HACK; }
+            s2.read = (int32_t)r;
+            s2.k0 = nk0;
+            s2.k0_rng = (nk0 + 7) & ~7;
+            s2.tile0 = (int32_t)ntile;
+            ntile += (s2.nk + T - 1) / T;
+            nk_total += s2.nk;
+            nseg++;
+            rd.nseg = 2;
+            rd.shift_len = (int)strlen(ADAPTOR_RNA) * (int)ctx->cfg.profile.dwell_mean;
+        }
+        if (ntile > 0x7FFFFFF0) return fail(ctx, SQG_ERR_ARG, "batch too large (tile count)");
+    }
+    s.h_ss_off.p[n_reads] = nk_total;
+    s.n_reads = n_reads; s.n_segs = nseg; s.n_tiles = ntile; s.total_kmers = nk_total;
+    s.total_bases = total_bases; s.first_read = first_read; s.want = want;
+
+    // device buffers + uploads
+    const bool fresh = s.d_bases.cap < (size_t)(CONST_REGION + total_bases + 16);
+    CU(s.d_bases.ensure((size_t)(CONST_REGION + total_bases + 16), false, s.stream));
+    if (fresh || !s.const_written) {
+        unsigned char c[CONST_REGION];
+        memset(c, 0, sizeof c);
+        memcpy(c + C_HACK, "ACGTACGTACGT", 12);
+        memcpy(c + C_DNA_PREFIX, STALL_DNA, strlen(STALL_DNA));
+        memcpy(c + C_DNA_PREFIX + strlen(STALL_DNA), ADAPTOR_DNA, strlen(ADAPTOR_DNA));
+        memset(c + C_RNA_SUFFIX, 'A', POLYA_LEN);
+        memcpy(c + C_RNA_SUFFIX + POLYA_LEN, ADAPTOR_RNA, strlen(ADAPTOR_RNA));
+        memcpy(c + C_RNA_STALL, STALL_RNA, strlen(STALL_RNA));
+        CU(cudaMemcpyAsync(s.d_bases.p, c, CONST_REGION, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaStreamSynchronize(s.stream));  // c is a stack buffer
+        s.const_written = true;
+    }
+    if (total_bases)
+        CU(cudaMemcpyAsync(s.d_bases.p + CONST_REGION, bases + user0, (size_t)total_bases, cudaMemcpyHostToDevice, s.stream));
+    CU(s.d_segs.ensure((size_t)std::max<int64_t>(nseg, 1), false, s.stream));
+    CU(s.d_reads.ensure((size_t)std::max<int64_t>(n_reads, 1), false, s.stream));
+    if (nseg) CU(cudaMemcpyAsync(s.d_segs.p, s.h_segs.p, (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s.stream));
+    if (n_reads) CU(cudaMemcpyAsync(s.d_reads.p, s.h_reads.p, (size_t)n_reads * sizeof(ReadDesc), cudaMemcpyHostToDevice, s.stream));
+    const size_t nt = (size_t)std::max<int64_t>(ntile, 1), nr = (size_t)std::max<int64_t>(n_reads, 1);
+    CU(s.d_tile_seg.ensure(nt, false, s.stream));
+    CU(s.d_tile_sum.ensure(nt, false, s.stream));
+    CU(s.d_tile_base.ensure(nt, false, s.stream));
+    CU(s.d_siglen.ensure(nr, false, s.stream));
+    CU(s.d_n0.ensure(nr, false, s.stream));
+    CU(s.d_sigoff.ensure(nr, false, s.stream));
+    CU(s.d_offset.ensure(nr, false, s.stream));
+    CU(s.d_median.ensure(nr, false, s.stream));
+    CU(s.d_meta.ensure(4, false, s.stream));
+    CU(s.h_meta.ensure(4));
+    if (want & SQG_WANT_SS) CU(s.d_ss.ensure((size_t)std::max<int64_t>(nk_total, 1), false, s.stream));
+    return SQG_OK;
+}
+
+GenParams slot_params(sqg_ctx *ctx, Slot &s) {
+    GenParams p = ctx->base;
+    p.bases = s.d_bases.p; p.segs = s.d_segs.p; p.reads = s.d_reads.p;
+    p.tile_seg = s.d_tile_seg.p; p.tile_sum = s.d_tile_sum.p; p.tile_base = s.d_tile_base.p;
+    p.read_siglen = s.d_siglen.p; p.read_n0 = s.d_n0.p; p.read_sigoff = s.d_sigoff.p;
+    p.read_offset = s.d_offset.p; p.read_median = s.d_median.p; p.meta = s.d_meta.p;
+    p.sig = s.d_sig.p; p.ss = s.d_ss.p;
+    p.n_reads = (int32_t)s.n_reads; p.n_segs = (int32_t)s.n_segs; p.n_tiles = (int32_t)s.n_tiles;
+    p.first_read = s.first_read;
+    p.want_ss = (s.want & SQG_WANT_SS) ? 1 : 0;
+    return p;
+}
+
+// K1-K3: lengths and offsets.  Asynchronous on the slot's stream.
+int slot_plan(sqg_ctx *ctx, Slot &s) {
+    if (s.n_reads == 0) return SQG_OK;
+    const GenParams p = slot_params(ctx, s);
+    CU(cudaMemsetAsync(s.d_meta.p, 0, 4 * sizeof(int64_t), s.stream));
+    if (ctx->rand_dwell) {
+        const int grid = (int)std::min<int64_t>(s.n_tiles, (int64_t)ctx->num_sms * 8);
+        dwell_sum_kernel<<<grid, K1_THREADS, 0, s.stream>>>(p);
+        ctx->launches++;
+    }
+    const int g2 = (int)((s.n_reads + 255) / 256);
+    if (ctx->rand_dwell) read_plan_kernel<true><<<g2, 256, 0, s.stream>>>(p);
+    else read_plan_kernel<false><<<g2, 256, 0, s.stream>>>(p);
+    read_offsets_kernel<<<1, 1024, 0, s.stream>>>(p);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return SQG_OK;
+}
+
+// read the totals back (one small D2H + sync) and make sure the signal arena is large enough
+int slot_size_arena(sqg_ctx *ctx, Slot &s) {
+    if (s.n_reads == 0) { s.arena_need = s.total_samples = 0; return SQG_OK; }
+    CU(cudaMemcpyAsync(s.h_meta.p, s.d_meta.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    if (s.h_meta.p[2]) return fail(ctx, SQG_ERR_RANGE, "a read has >= UINT32_MAX samples (reference: src/sim.c:559-562)");
+    s.arena_need = s.h_meta.p[0];
+    s.total_samples = s.h_meta.p[1];
+    CU(s.d_sig.ensure((size_t)std::max<int64_t>(s.arena_need, 64), false, s.stream));
+    return SQG_OK;
+}
+
+// K4 (+ the RNA prefix shift).  Asynchronous.
+int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr) {
+    if (s.n_reads == 0) return SQG_OK;
+    const GenParams p = slot_params(ctx, s);
+    const int grid = (int)std::min<int64_t>(s.n_tiles, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    if (before) CU(cudaEventRecord(before, s.stream));
+    void *args[] = {(void *)&p};
+    CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(K4_THREADS), args, ctx->k4_smem, s.stream));
+    if (after) CU(cudaEventRecord(after, s.stream));
+    ctx->launches++;
+    if (ctx->prefix && ctx->rev) {
+        prefix_shift_kernel<<<(int)s.n_reads, 256, 0, s.stream>>>(p);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return SQG_OK;
+}
+
+// D2H of everything the caller gets back; fills *res.  Synchronises the slot's stream.
+int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
+    const size_t n = (size_t)s.n_reads;
+    CU(s.h_siglen.ensure(n + 1));
+    CU(s.h_sigoff.ensure(n + 1));
+    CU(s.h_len64.ensure(n + 1));
+    CU(s.h_offset.ensure(n + 1));
+    CU(s.h_median.ensure(n + 1));
+    CU(s.h_sig.ensure((size_t)std::max<int64_t>(s.arena_need, 64)));
+    if (n) {
+        CU(cudaMemcpyAsync(s.h_sig.p, s.d_sig.p, (size_t)s.arena_need * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_siglen.p, s.d_siglen.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_sigoff.p, s.d_sigoff.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_offset.p, s.d_offset.p, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_median.p, s.d_median.p, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (s.want & SQG_WANT_SS) {
+            CU(s.h_ss.ensure((size_t)std::max<int64_t>(s.total_kmers, 1)));
+            CU(cudaMemcpyAsync(s.h_ss.p, s.d_ss.p, (size_t)s.total_kmers * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    CU(cudaStreamSynchronize(s.stream));
+    for (size_t i = 0; i < n; i++) s.h_len64.p[i] = (int64_t)s.h_siglen.p[i];
+    if (res) {
+        res->n_reads = s.n_reads;
+        res->total_samples = s.total_samples;
+        res->signal = s.h_sig.p;
+        res->sig_off = s.h_sigoff.p;
+        res->len_raw_signal = s.h_len64.p;
+        res->offset = s.h_offset.p;
+        res->median_before = s.h_median.p;
+        res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
+        res->ss_off = s.h_ss_off.p;
+    }
+    return SQG_OK;
+}
+
+int slot_run_all(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, const int64_t *base_off,
+                 int64_t first_read, uint32_t want, sqg_result_t *res) {
+    int rc;
+    if ((rc = slot_prepare(ctx, s, n_reads, bases, base_off, first_read, want)) != SQG_OK) return rc;
+    if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
+    if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
+    if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
+    return slot_fetch(ctx, s, res);
+}
+
+void worker_main(sqg_ctx *ctx, int slot_idx) {
+    cudaSetDevice(ctx->device);
+    for (;;) {
+        Job *job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(ctx->mu);
+            ctx->cv_work.wait(lk, [&] { return ctx->stopping || !ctx->queues[slot_idx].empty(); });
+            if (ctx->stopping && ctx->queues[slot_idx].empty()) return;
+            job = ctx->queues[slot_idx].front();
+            ctx->queues[slot_idx].pop_front();
+        }
+        // NB: ctx->err is shared; jobs report through their status code
+        int rc = slot_run_all(ctx, ctx->slots[slot_idx], job->n_reads, job->bases, job->base_off, job->first_read,
+                              job->want, nullptr);
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            job->status = rc;
+        }
+        ctx->cv_done.notify_all();
+    }
+}
+
+int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
+    ctx->cfg = *cfg;
+    const sqg_profile_t &pr = cfg->profile;
+    if (cfg->kmer_size < 1 || cfg->kmer_size > 9) return fail(ctx, SQG_ERR_ARG, "kmer_size must be 1..9 (MAX_KMER_SIZE, src/sq.h:17)");
+    uint64_t expect = 1;
+    for (uint32_t i = 0; i < cfg->kmer_size; i++) expect *= cfg->meth ? 5 : 4;
+    if (cfg->num_kmer != expect) return fail(ctx, SQG_ERR_ARG, "num_kmer must be 4^k (or 5^k with meth)");
+    if (!(pr.range > 0) || !(pr.digitisation > 0) || !(pr.dwell_mean >= 1) || pr.dwell_std < 0)
+        return fail(ctx, SQG_ERR_ARG, "profile: need range>0, digitisation>0, dwell_mean>=1, dwell_std>=0");
+    if (cfg->rng_mode != SQG_RNG_PHILOX && cfg->rng_mode != SQG_RNG_LEGACY) return fail(ctx, SQG_ERR_ARG, "unknown rng_mode");
+    if (cfg->rng_mode == SQG_RNG_LEGACY) return fail(ctx, SQG_ERR_ARG, "SQG_RNG_LEGACY is not available in this build");
+
+    const bool ideal = cfg->flags & SQG_IDEAL;
+    ctx->noisy = !(ideal || (cfg->flags & SQG_IDEAL_AMP));
+    // dwell_std == 0 makes round(N(mean,0)) a constant (rna004 presets, src/sim.c:136-137)
+    const bool fixed = ideal || (cfg->flags & SQG_IDEAL_TIME);
+    ctx->rand_dwell = !fixed;
+    ctx->meth = cfg->meth != 0;
+    ctx->rev = cfg->flags & SQG_RNA;
+    ctx->prefix = cfg->flags & SQG_PREFIX;
+
+    GenParams &b = ctx->base;
+    memset(&b, 0, sizeof b);
+    b.k = (int32_t)cfg->kmer_size;
+    b.num_kmer = cfg->num_kmer;
+    if (cfg->meth) {
+        uint32_t p5 = 1;
+        for (uint32_t i = 0; i + 1 < cfg->kmer_size; i++) p5 *= 5;
+        b.kmask = p5;
+    } else {
+        b.kmask = (uint32_t)((1ull << (2 * cfg->kmer_size)) - 1);
+    }
+    b.digitisation = pr.digitisation; b.range = pr.range; b.scale = pr.digitisation / pr.range;
+    b.offset_mean = pr.offset_mean; b.offset_std = pr.offset_std;
+    b.median_mean = pr.median_before_mean; b.median_std = pr.median_before_std;
+    b.dwell_mean = pr.dwell_mean; b.dwell_std = pr.dwell_std;
+    b.sps_fixed = (int32_t)pr.dwell_mean;
+    b.ideal = ideal ? 1 : 0;
+    b.amp_noise = cfg->amp_noise;
+    b.key0 = (uint32_t)((uint64_t)cfg->seed & 0xFFFFFFFFu);
+    b.key1 = (uint32_t)((uint64_t)cfg->seed >> 32);
+    b.shift_val = (int32_t)(int16_t)(30 * pr.digitisation / pr.range);  // src/genread.c:82
+
+    if (ctx->rand_dwell) {
+        if (pr.dwell_std == 0.0) {
+            // constant dwell: no draw needed, but it is round(dwell_mean), not (int)dwell_mean
+            int d = (int)std::round(pr.dwell_mean);
+            if (d < 1) d = -d + 1;
+            b.sps_fixed = d;
+            ctx->rand_dwell = false;
+        }
+    }
+    if (ctx->rand_dwell) {
+        const double mx = std::floor(pr.dwell_mean + (double)Z_MAX * pr.dwell_std + 0.5) + 1.0;
+        if (!(mx < 8000.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 5.72*dwell_std too large for one tile");
+        int T = (int)((MAP_CAP * 8 - 16) / (int)mx) & ~7;
+        b.T = std::max(8, std::min(T, MAX_T));
+    } else {
+        b.T = MAX_T;
+    }
+    return SQG_OK;
+}
+
+int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_model_in) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(ctx, SQG_ERR_NODEVICE, "no CUDA device: libsqg has no CPU fallback");
+    if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) return fail(ctx, SQG_ERR_ARG, "bad device ordinal");
+    ctx->device = ctx->cfg.device;
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major < 10) return fail(ctx, SQG_ERR_NODEVICE, "libsqg is built for sm_100a (B200) only");
+    ctx->num_sms = prop.multiProcessorCount;
+    const size_t n = ctx->cfg.num_kmer;
+    CU(ctx->d_model.ensure(n));
+    if (h_model) CU(cudaMemcpy(ctx->d_model.p, h_model, n * sizeof(float2), cudaMemcpyHostToDevice));
+    else CU(cudaMemcpy(ctx->d_model.p, d_model_in, n * sizeof(float2), cudaMemcpyDeviceToDevice));
+    CU(ctx->d_z.ensure(Z1_N + 16 * Z2_SUB));
+    CU(cudaMemcpy(ctx->d_z.p, sqg_ztable_blob, (Z1_N + 16 * Z2_SUB) * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->base.model = ctx->d_model.p;
+    ctx->base.z1 = ctx->d_z.p;
+    ctx->base.z2 = ctx->d_z.p + Z1_N;
+
+    // shared-memory plan of the signal kernel: tile state + quantile table (+ the pore model when it is small:
+    // R9 6-mer = 32 KB, R9 RNA 5-mer = 8 KB)
+    const bool use_z = ctx->noisy || ctx->rand_dwell;
+    size_t smem = ((sizeof(TileSmem) + 127) & ~(size_t)127) + (use_z ? Z1_N * 4 : 0);
+    ctx->model_in_smem = (!ctx->meth && n <= 4096) ? 1 : 0;
+    if (ctx->model_in_smem) smem += n * sizeof(float2);
+    ctx->base.model_in_smem = ctx->model_in_smem;
+    ctx->k4_smem = smem;
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, K4_THREADS, smem));
+    if (occ < 1) return fail(ctx, SQG_ERR_CUDA, "signal kernel does not fit on an SM");
+    ctx->k4_grid_per_sm = occ;
+
+    int rc = slot_init(ctx, ctx->sync_slot);
+    if (rc != SQG_OK) return rc;
+    return SQG_OK;
+}
+
+int init_common(sqg_ctx **out, const sqg_config_t *cfg, const sqg_model_t *h_model, const void *d_model) {
+    if (!out || !cfg || (!h_model && !d_model)) return fail(nullptr, SQG_ERR_ARG, "null argument");
+    *out = nullptr;
+    sqg_ctx *ctx = new (std::nothrow) sqg_ctx();
+    if (!ctx) return fail(nullptr, SQG_ERR_NOMEM, "out of host memory");
+    int rc = ctx_setup(ctx, cfg);
+    if (rc == SQG_OK) rc = ctx_device_setup(ctx, h_model, d_model);
+    if (rc != SQG_OK) {
+        g_init_error = ctx->err;
+        sqg_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SQG_OK;
+}
+
+int ensure_dispatcher(sqg_ctx *ctx) {
+    if (!ctx->slots.empty()) return SQG_OK;
+    const int n = ctx->cfg.n_slots > 0 ? std::min(ctx->cfg.n_slots, 16) : 3;
+    ctx->slots.resize(n);
+    ctx->queues.resize(n);
+    ctx->slot_busy.assign(n, 0);
+    for (int i = 0; i < n; i++) {
+        int rc = slot_init(ctx, ctx->slots[i]);
+        if (rc != SQG_OK) return rc;
+    }
+    for (int i = 0; i < n; i++) ctx->workers.emplace_back(worker_main, ctx, i);
+    return SQG_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *sqg_version(void) { return "squigulator-b200 0.1.0 (sm_100a)"; }
+
+const char *sqg_last_error(const sqg_ctx_t *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int sqg_init(sqg_ctx_t **ctx, const sqg_config_t *cfg, const sqg_model_t *model) {
+    return init_common(ctx, cfg, model, nullptr);
+}
+
+int sqg_init_device_model(sqg_ctx_t **ctx, const sqg_config_t *cfg, const void *d_model) {
+    return init_common(ctx, cfg, nullptr, d_model);
+}
+
+void sqg_destroy(sqg_ctx_t *ctx) {
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stopping = true;
+    }
+    ctx->cv_work.notify_all();
+    for (auto &t : ctx->workers) t.join();
+    cudaSetDevice(ctx->device);
+    for (auto &kv : ctx->jobs) delete kv.second;
+    for (auto &s : ctx->slots) s.release();
+    ctx->sync_slot.release();
+    ctx->d_model.release();
+    ctx->d_z.release();
+    delete ctx;
+}
+
+void *sqg_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void sqg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                  int64_t first_read_index, uint32_t want, sqg_result_t *res) {
+    if (!ctx || !res) return SQG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    return slot_run_all(ctx, ctx->sync_slot, n_reads, bases, base_off, first_read_index, want, res);
+}
+
+int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+               int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket) {
+    if (!ctx || !ticket) return SQG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_dispatcher(ctx);
+    if (rc != SQG_OK) return rc;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    int slot = -1;
+    ctx->cv_done.wait(lk, [&] {
+        for (size_t i = 0; i < ctx->slot_busy.size(); i++)
+            if (!ctx->slot_busy[i]) { slot = (int)i; return true; }
+        return false;
+    });
+    Job *job = new Job{ctx->next_ticket++, slot, n_reads, bases, base_off, first_read_index, want, 1};
+    ctx->slot_busy[slot] = 1;
+    ctx->jobs[job->ticket] = job;
+    ctx->queues[slot].push_back(job);
+    *ticket = job->ticket;
+    lk.unlock();
+    ctx->cv_work.notify_all();
+    return SQG_OK;
+}
+
+int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res) {
+    if (!ctx) return SQG_ERR_ARG;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    auto it = ctx->jobs.find(ticket);
+    if (it == ctx->jobs.end()) return fail(ctx, SQG_ERR_STATE, "unknown ticket");
+    Job *job = it->second;
+    ctx->cv_done.wait(lk, [&] { return job->status <= 0; });
+    if (job->status != SQG_OK) return job->status;
+    if (res) {
+        Slot &s = ctx->slots[job->slot];
+        res->n_reads = s.n_reads;
+        res->total_samples = s.total_samples;
+        res->signal = s.h_sig.p;
+        res->sig_off = s.h_sigoff.p;
+        res->len_raw_signal = s.h_len64.p;
+        res->offset = s.h_offset.p;
+        res->median_before = s.h_median.p;
+        res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
+        res->ss_off = s.h_ss_off.p;
+    }
+    return SQG_OK;
+}
+
+int sqg_release(sqg_ctx_t *ctx, sqg_ticket_t ticket) {
+    if (!ctx) return SQG_ERR_ARG;
+    {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        auto it = ctx->jobs.find(ticket);
+        if (it == ctx->jobs.end()) return fail(ctx, SQG_ERR_STATE, "unknown ticket");
+        Job *job = it->second;
+        ctx->cv_done.wait(lk, [&] { return job->status <= 0; });
+        ctx->slot_busy[job->slot] = 0;
+        ctx->jobs.erase(it);
+        delete job;
+    }
+    ctx->cv_done.notify_all();
+    return SQG_OK;
+}
+
+int16_t *sqg_gen_sig(sqg_ctx_t *ctx, const char *read, int32_t len, double *offset, double *median_before,
+                     int64_t *len_raw_signal, int64_t read_index, int32_t **ss, int64_t *ss_n) {
+    if (!ctx || !read || len < 0) return nullptr;
+    const int64_t off[2] = {0, len};
+    sqg_result_t res;
+    if (sqg_gen_batch(ctx, 1, read, off, read_index, ss ? SQG_WANT_SS : 0, &res) != SQG_OK) return nullptr;
+    const int64_t n = res.len_raw_signal[0];
+    int16_t *out = (int16_t *)malloc((size_t)std::max<int64_t>(n, 1) * sizeof(int16_t));
+    if (!out) return nullptr;
+    memcpy(out, res.signal + res.sig_off[0], (size_t)n * sizeof(int16_t));
+    if (offset) *offset = res.offset[0];
+    if (median_before) *median_before = res.median_before[0];
+    if (len_raw_signal) *len_raw_signal = n;
+    if (ss) {
+        const int64_t nk = res.ss_off[1] - res.ss_off[0];
+        *ss = (int32_t *)malloc((size_t)std::max<int64_t>(nk, 1) * sizeof(int32_t));
+        if (*ss) memcpy(*ss, res.ss, (size_t)nk * sizeof(int32_t));
+        if (ss_n) *ss_n = nk;
+    }
+    return out;
+}
+
+// ---- device-resident batches ----
+
+int sqg_dev_batch_create(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                         int64_t first_read_index, uint32_t want, sqg_dev_batch_t **batch) {
+    if (!ctx || !batch) return SQG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    sqg_dev_batch *b = new (std::nothrow) sqg_dev_batch();
+    if (!b) return fail(ctx, SQG_ERR_NOMEM, "out of host memory");
+    int rc = slot_init(ctx, b->slot);
+    if (rc == SQG_OK) rc = slot_prepare(ctx, b->slot, n_reads, bases, base_off, first_read_index, want);
+    if (rc == SQG_OK) {
+        cudaError_t e = cudaStreamSynchronize(b->slot.stream);
+        if (e != cudaSuccess) rc = fail(ctx, SQG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc != SQG_OK) {
+        b->slot.release();
+        delete b;
+        return rc;
+    }
+    *batch = b;
+    return SQG_OK;
+}
+
+int sqg_dev_batch_run(sqg_ctx_t *ctx, sqg_dev_batch_t *b, int32_t steps, float *ms_total, float *ms_signal_kernel) {
+    if (!ctx || !b || steps < 1) return SQG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Slot &s = b->slot;
+    int rc;
+    if (!b->planned) {  // first (untimed) plan sizes the arena; the plan is deterministic, so it holds for every step
+        if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
+        if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
+        b->planned = true;
+    }
+    while ((int)s.kev.size() < 2 * steps) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        s.kev.push_back(e);
+    }
+    CU(cudaEventRecord(s.ev0, s.stream));
+    for (int i = 0; i < steps; i++) {
+        if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
+        if ((rc = slot_generate(ctx, s, s.kev[2 * i], s.kev[2 * i + 1])) != SQG_OK) return rc;
+    }
+    CU(cudaEventRecord(s.ev1, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    if (ms_total) CU(cudaEventElapsedTime(ms_total, s.ev0, s.ev1));
+    if (ms_signal_kernel) {
+        float acc = 0.f;
+        for (int i = 0; i < steps; i++) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, s.kev[2 * i], s.kev[2 * i + 1]));
+            acc += t;
+        }
+        *ms_signal_kernel = acc;
+    }
+    return SQG_OK;
+}
+
+int sqg_dev_batch_info(sqg_ctx_t *ctx, sqg_dev_batch_t *b, int64_t *total_samples, int64_t *total_kmers,
+                       int64_t *total_bases, int64_t *kernel_launches) {
+    if (!ctx || !b) return SQG_ERR_ARG;
+    if (total_samples) *total_samples = b->slot.total_samples;
+    if (total_kmers) *total_kmers = b->slot.total_kmers;
+    if (total_bases) *total_bases = b->slot.total_bases;
+    if (kernel_launches) *kernel_launches = ctx->launches.load();
+    return SQG_OK;
+}
+
+int sqg_dev_batch_fetch(sqg_ctx_t *ctx, sqg_dev_batch_t *b, sqg_result_t *res) {
+    if (!ctx || !b || !res) return SQG_ERR_ARG;
+    if (!b->planned) return fail(ctx, SQG_ERR_STATE, "batch has not been run");
+    CU(cudaSetDevice(ctx->device));
+    return slot_fetch(ctx, b->slot, res);
+}
+
+void sqg_dev_batch_destroy(sqg_ctx_t *ctx, sqg_dev_batch_t *b) {
+    if (!b) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    b->slot.release();
+    delete b;
+}
+
+int sqg_bench_store(sqg_ctx_t *ctx, size_t bytes, int32_t steps, float *ms_total) {
+    if (!ctx || !ms_total || steps < 1) return SQG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    Slot &s = ctx->sync_slot;
+    const size_t n16 = bytes / 16;
+    CU(s.d_sig.ensure(n16 * 8, false, s.stream));
+    CU(cudaEventRecord(s.ev0, s.stream));
+    for (int i = 0; i < steps; i++) {
+        store_only_kernel<<<ctx->num_sms * 4, 512, 0, s.stream>>>(reinterpret_cast<uint4 *>(s.d_sig.p), n16);
+        ctx->launches++;
+    }
+    CU(cudaEventRecord(s.ev1, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    CU(cudaEventElapsedTime(ms_total, s.ev0, s.ev1));
+    return SQG_OK;
+}
+
+int64_t sqg_launch_count(const sqg_ctx_t *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+}  // extern "C"

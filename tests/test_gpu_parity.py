@@ -1,0 +1,172 @@
+"""GPU parity: libsqg.so (through the C ABI) against the CPU oracle and the reference goldens.
+
+Bar: bit-exact int16 signals, bit-exact per-read doubles, equal dwell arrays."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sq():
+    import squigulator_b200 as s
+    s.load_library()
+    return s
+
+
+def run_pair(sq, oracle_lib, ztable, profile, flags, k, reads, seed=11, meth=False, amp_noise=1.0, first=0, want_ss=True,
+             model=None):
+    num_kmer = (5 if meth else 4) ** k
+    model = H.random_model(num_kmer) if model is None else model
+    gen = sq.SignalGenerator(dict(profile), model, k, flags=flags, seed=seed, meth=meth, amp_noise=amp_noise)
+    got = gen.gen_batch(reads, first_read_index=first, want_ss=want_ss)
+    gen.close()
+    o = H.Oracle(oracle_lib, profile, flags, k, num_kmer, model, seed, H.RNG_PHILOX, meth=int(meth), amp_noise=amp_noise,
+                 ztable=ztable)
+    for i, read in enumerate(reads):
+        exp = o.gen_sig(read, read_index=first + i, want_ss=want_ss)
+        assert len(got[i]["sig"]) == len(exp["sig"]), f"read {i}: length {len(got[i]['sig'])} != {len(exp['sig'])}"
+        if want_ss:
+            np.testing.assert_array_equal(got[i]["ss"], exp["ss"], err_msg=f"read {i} dwell")
+        bad = np.nonzero(got[i]["sig"] != exp["sig"])[0]
+        assert bad.size == 0, f"read {i}: {bad.size} samples differ, first at {bad[:5]} got {got[i]['sig'][bad[:5]]} exp {exp['sig'][bad[:5]]}"
+        assert got[i]["offset"] == exp["offset"] and got[i]["median_before"] == exp["median_before"], f"read {i} per-read draws"
+    o.close()
+    return got
+
+
+CASES = [
+    # name, preset, extra flags, k, meth, read alphabet, mean len, n
+    ("dna_r9_prom", "dna-r9-prom", 0, 6, False, b"ACGT", 3000, 40),
+    ("dna_r9_min", "dna-r9-min", 0, 6, False, b"ACGT", 2000, 20),
+    ("dna_r10_prom", "dna-r10-prom", 0, 9, False, b"ACGT", 5000, 40),
+    ("rna_r9_prom", "rna-r9-prom", 0, 5, False, b"ACGT", 1200, 30),
+    ("rna004_prom", "rna004-prom", 0, 9, False, b"ACGT", 1300, 30),
+    ("dna_ideal", "dna-r9-prom", H.SQ_IDEAL, 6, False, b"ACGT", 3000, 20),
+    ("dna_ideal_time", "dna-r10-prom", H.SQ_IDEAL_TIME, 9, False, b"ACGT", 3000, 20),
+    ("dna_ideal_amp", "dna-r10-prom", H.SQ_IDEAL_AMP, 9, False, b"ACGT", 3000, 20),
+    ("rna_ideal", "rna004-prom", H.SQ_IDEAL, 9, False, b"ACGT", 1000, 20),
+    ("rna_ideal_amp", "rna-r9-prom", H.SQ_IDEAL_AMP, 5, False, b"ACGT", 900, 20),
+    ("r9_meth", "dna-r9-prom", 0, 6, True, b"ACGTM", 3000, 20),
+    ("r10_meth", "dna-r10-prom", 0, 9, True, b"ACGTM", 3000, 12),
+    ("iupac_lower_n", "dna-r9-prom", 0, 6, False, b"ACGTacgtNnRYKMSWBDHVU", 2000, 20),
+    ("dna_prefix", "dna-r9-prom", H.SQ_PREFIX, 6, False, b"ACGT", 2000, 12),
+    ("rna_prefix", "rna-r9-prom", H.SQ_PREFIX, 5, False, b"ACGT", 900, 12),
+    ("rna004_prefix", "rna004-prom", H.SQ_PREFIX, 9, False, b"ACGT", 900, 12),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_gpu_equals_oracle(case, sq, oracle_lib, ztable):
+    name, preset, xflags, k, meth, alpha, mean_len, n = case
+    prof, pflags = H.PRESETS[preset]
+    reads = H.random_reads(n, mean_len, seed=hash(name) & 0xFFFF, alphabet=alpha)
+    run_pair(sq, oracle_lib, ztable, prof, pflags | xflags, k, reads, meth=meth, first=1000)
+
+
+def test_edge_cases(sq, oracle_lib, ztable):
+    prof, pflags = H.PRESETS["dna-r10-prom"]
+    # empty read, reads shorter than k (the "ACGTACGTACGT" rule, reference src/gensig.c:242-245), len == k, len == k+1
+    reads = [b"", b"A", b"ACGTACG", b"ACGTACGTA", b"ACGTACGTAC", b"T" * 5000, b"ACGT" * 3000]
+    run_pair(sq, oracle_lib, ztable, prof, pflags, 9, reads, first=7)
+    prof, pflags = H.PRESETS["rna-r9-prom"]
+    run_pair(sq, oracle_lib, ztable, prof, pflags, 5, [b"", b"AC", b"ACGTA", b"ACGTAC", b"G" * 3000], first=3)
+    run_pair(sq, oracle_lib, ztable, prof, pflags | H.SQ_PREFIX, 5, [b"", b"AC", b"G" * 700], first=3)
+
+
+def test_empty_batch(sq):
+    gen = sq.SignalGenerator("dna-r9-prom", H.random_model(4096), 6)
+    assert gen.gen_batch([]) == []
+    gen.close()
+
+
+def test_large_read_index_and_seed(sq, oracle_lib, ztable):
+    prof, pflags = H.PRESETS["dna-r9-prom"]
+    reads = H.random_reads(6, 1500, seed=5)
+    run_pair(sq, oracle_lib, ztable, prof, pflags, 6, reads, seed=(1 << 40) + 12345, first=(1 << 33) + 5)
+
+
+def test_dwell_extremes(sq, oracle_lib, ztable):
+    # large spread: many folded (negative) draws; dwell_std = 0 with non-integer mean; --amp-noise scaling
+    prof = dict(H.PRESETS["dna-r9-prom"][0])
+    prof["dwell_mean"], prof["dwell_std"] = 4.0, 9.0
+    run_pair(sq, oracle_lib, ztable, prof, 0, 6, H.random_reads(10, 1500, seed=9))
+    prof["dwell_mean"], prof["dwell_std"] = 7.5, 0.0
+    run_pair(sq, oracle_lib, ztable, prof, 0, 6, H.random_reads(10, 1500, seed=10))
+    prof["dwell_mean"], prof["dwell_std"] = 120.0, 60.0
+    run_pair(sq, oracle_lib, ztable, prof, 0, 6, H.random_reads(4, 800, seed=12), amp_noise=0.5)
+    run_pair(sq, oracle_lib, ztable, H.PRESETS["dna-r10-min"][0], H.SQ_R10, 9, H.random_reads(6, 2500, seed=13), amp_noise=0.0)
+
+
+def test_batch_split_and_api_variants_agree(sq):
+    """Output depends only on (seed, global read index, bases): not on batching, nor on which entry point is used."""
+    reads = H.random_reads(24, 2500, seed=21, min_len=0)
+    model = H.random_model(4 ** 9)
+    gen = sq.SignalGenerator("dna-r10-prom", model, 9, seed=5, n_slots=2)
+    whole = gen.gen_batch(reads, first_read_index=100, want_ss=True)
+    a = gen.gen_batch(reads[:9], first_read_index=100, want_ss=True)
+    b = gen.gen_batch(reads[9:], first_read_index=109, want_ss=True)
+    for x, y in zip(whole, a + b):
+        np.testing.assert_array_equal(x["sig"], y["sig"])
+        np.testing.assert_array_equal(x["ss"], y["ss"])
+        assert x["offset"] == y["offset"] and x["median_before"] == y["median_before"]
+    # per-read drop-in (gen_sig shape)
+    for i in (0, 5, 23):
+        r = gen.gen_sig(reads[i], read_index=100 + i, want_ss=True)
+        np.testing.assert_array_equal(r["sig"], whole[i]["sig"])
+        np.testing.assert_array_equal(r["ss"], whole[i]["ss"])
+        assert r["offset"] == whole[i]["offset"]
+    # asynchronous dispatcher: three batches in flight over two slots
+    from squigulator_b200.api import _pack_reads, WANT_SS
+    parts = [(reads[:8], 100), (reads[8:16], 108), (reads[16:], 116)]
+    packed = [(_pack_reads(r), f) for r, f in parts]
+    tickets = [gen.submit(p[0], p[1], first_read_index=f, want=WANT_SS) for p, f in packed[:2]]
+    got = []
+    res = gen.wait(tickets[0]); got += gen._unpack(res); gen.release(tickets[0])
+    tickets.append(gen.submit(packed[2][0][0], packed[2][0][1], first_read_index=packed[2][1], want=WANT_SS))
+    for t in tickets[1:]:
+        res = gen.wait(t); got += gen._unpack(res); gen.release(t)
+    for x, y in zip(whole, got):
+        np.testing.assert_array_equal(x["sig"], y["sig"])
+    # device-resident batch (what bench.py times)
+    (bases, off) = _pack_reads(reads)
+    db = gen.dev_batch(bases, off, first_read_index=100)
+    gen.dev_batch_run(db, 2)
+    for x, y in zip(whole, gen.dev_batch_fetch(db)):
+        np.testing.assert_array_equal(x["sig"], y["sig"])
+    assert gen.dev_batch_info(db)["samples"] == sum(len(x["sig"]) for x in whole)
+    gen.dev_batch_destroy(db)
+    assert gen.launch_count() > 0
+    gen.close()
+
+
+@pytest.mark.parametrize("name", ["dna_ideal"])
+def test_gpu_reproduces_reference_ideal_golden(name, sq):
+    """--ideal uses no random numbers, so the GPU output must equal the reference's own golden file
+    (reference test/dna_ideal_slow5.exp via tests/golden/dna_ideal.npz) bit for bit."""
+    g = H.Golden(os.path.join(H.GOLDEN_DIR, name + ".npz"))
+    c = g.cfg
+    gen = sq.SignalGenerator(c["profile"], g.dense_model(), c["kmer_size"], flags=c["flags"], seed=c["seed"],
+                             meth=bool(c["meth"]), amp_noise=c["amp_noise"])
+    got = gen.gen_batch(g.reads)
+    gen.close()
+    for i in range(len(g.reads)):
+        assert len(got[i]["sig"]) == g.sig_len[i]
+        assert H.sha256_i16(got[i]["sig"]) == g.sha_of(i)
+        if i < g.n_full:
+            np.testing.assert_array_equal(got[i]["sig"], g.sig_full[i])
+        assert abs(got[i]["offset"] - g.offset[i]) < 1e-6 and abs(got[i]["median_before"] - g.median_before[i]) < 1e-6
+
+
+def test_golden_structure_philox(sq):
+    """Goldens with one noise source off pin structure even under Philox: --ideal-time fixes every length."""
+    g = H.Golden(os.path.join(H.GOLDEN_DIR, "dna_ideal_time.npz"))
+    c = g.cfg
+    gen = sq.SignalGenerator(c["profile"], g.dense_model(), c["kmer_size"], flags=c["flags"], seed=c["seed"])
+    got = gen.gen_batch(g.reads)
+    gen.close()
+    assert [len(x["sig"]) for x in got] == list(g.sig_len)
