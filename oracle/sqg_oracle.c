@@ -98,24 +98,47 @@ void sqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 /* counter word 3 = stream tag */
 enum { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
 
-#define Z1_N 32768
+#define Z16_N 65536
 #define Z_TAIL_FIRST 32752
 #define Z2_SUB 1024
 
-/* 16-bit uniform -> N(0,1) by quantile table; the 16 outermost cells take 10 more bits from a
- * dedicated Philox block addressed by (c0,c1,c2,tail_stream).  DESIGN.md "z16". */
-float sqo_z16(const float *zt, uint32_t h, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
+/* IEEE binary16 -> binary32, exact */
+static float half_to_float(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu, bits;
+    if (e == 0) {
+        if (m == 0) {
+            bits = sign;
+        } else { /* subnormal: normalise */
+            int sh = 0;
+            while (!(m & 0x400u)) { m <<= 1; sh++; }
+            bits = sign | ((uint32_t)(113 - sh) << 23) | ((m & 0x3FFu) << 13);
+        }
+    } else if (e == 31) {
+        bits = sign | 0x7F800000u | (m << 13);
+    } else {
+        bits = sign | ((e + 112) << 23) | (m << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+/* 16-bit uniform -> N(0,1) by quantile table (bit 15 = sign, bits 0-14 = half-normal cell); the 16
+ * outermost cells take 10 more bits from a dedicated Philox block addressed by (c0,c1,c2,tail_stream).
+ * zt = the bytes of squigulator_b200/data/ztable_v2.bin: Z16[65536] binary16, then Z2[16384] binary32.
+ * DESIGN.md "z16". */
+float sqo_z16(const void *zt, uint32_t h, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
               uint32_t tail_stream) {
+    const uint16_t *z16 = (const uint16_t *)zt;
+    const float *z2 = (const float *)((const unsigned char *)zt + Z16_N * 2);
     uint32_t i = h & 0x7FFFu;
-    float z;
     if (i >= Z_TAIL_FIRST) {
         uint32_t ctr[4] = {c0, c1, c2, tail_stream}, w[4];
         sqo_philox4x32_10(ctr, key, w);
-        z = zt[Z1_N + (i - Z_TAIL_FIRST) * Z2_SUB + (w[0] & (Z2_SUB - 1))];
-    } else {
-        z = zt[i];
+        float z = z2[(i - Z_TAIL_FIRST) * Z2_SUB + (w[0] & (Z2_SUB - 1))];
+        return (h & 0x8000u) ? -z : z;
     }
-    return (h & 0x8000u) ? -z : z;
+    return half_to_float(z16[h & 0xFFFFu]);
 }
 
 static uint32_t halfword(const uint32_t w[4], uint32_t j) { /* j in 0..7 */
@@ -133,12 +156,12 @@ typedef struct {
 typedef struct {
     sqo_config_t cfg;
     float *mean, *sd_eff; /* level_mean; level_stdv*amp_noise as a FLOAT product (src/sim.c:249) */
-    const float *zt;
+    const void *zt;
     uint32_t key[2];
     legacy_streams_t *ls;
 } oracle_t;
 
-void *sqo_open(const sqo_config_t *cfg, const float *model, const float *ztable) {
+void *sqo_open(const sqo_config_t *cfg, const float *model, const void *ztable) {
     oracle_t *o = (oracle_t *)calloc(1, sizeof(oracle_t));
     o->cfg = *cfg;
     uint32_t n = cfg->num_kmer;
@@ -317,9 +340,10 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
     for (int64_t i = 0; i < nk; i++) {
         int d = (int)p->dwell_mean;
         if (!fixed_dwell) {
-            double x;
             if (legacy) {
-                x = sqo_lehmer_normal(&ls->dwell, p->dwell_mean, p->dwell_std);
+                d = (int)round(sqo_lehmer_normal(&ls->dwell, p->dwell_mean, p->dwell_std));
+            } else if (p->dwell_std == 0.0) {
+                d = (int)round(p->dwell_mean); /* round(N(mean, 0)) is a constant (rna004 presets) */
             } else {
                 /* draw index: position in the read's k-mer list; a 2nd segment (RNA stall) starts at
                  * the next multiple of 8 so that every block of 8 draws lies inside one segment */
@@ -328,10 +352,10 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                 sqo_philox4x32_10(ctr, o->key, w);
                 float z = sqo_z16(o->zt, halfword(w, (uint32_t)(di & 7)), o->key, (uint32_t)di, r_lo, r_hi,
                                   ST_DWELL_TAIL);
-                double t = (double)z * p->dwell_std;
-                x = t + p->dwell_mean;
+                /* Philox mode: single-precision FMA, round to nearest (ties to even; the reference's
+                 * round() differs only on exact .5 ties, which table normals do not produce) */
+                d = (int)lrintf(fmaf(z, (float)p->dwell_std, (float)p->dwell_mean));
             }
-            d = (int)round(x);
             if (d < 1) d = -d + 1;
         }
         sps[i] = d;

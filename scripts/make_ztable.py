@@ -15,7 +15,11 @@ Z2[t*1024+j] = conditional RMS again, which keeps the variance exact and extends
 ~5.8 sigma (the reference's Box-Muller on a 31-bit Lehmer uniform reaches 6.55 sigma,
 /root/reference src/rand.h:79-94).
 
-Output: squigulator_b200/data/ztable_v1.bin = float32 LE, Z1 (32768) followed by Z2 (16384).
+Output: squigulator_b200/data/ztable_v2.bin =
+    Z16[65536] float16 LE : Z16[h] = (h & 0x8000 ? -1 : +1) * fp16(Z1[h & 0x7FFF])  (2-byte entries let the
+                            128 KB table sit in shared memory with the sign folded into the index; the
+                            fp16 rounding error, <= 2^-12 relative and zero-mean, is far below one ADC step)
+    Z2[16384]  float32 LE : the refined tail cells (magnitude; the sign comes from h)
 The file is data shared by the product (embedded into libsqg.so) and by the oracle (loaded at run
 time); tests/test_ztable.py re-derives it independently with mpmath.
 """
@@ -75,13 +79,18 @@ def build():
 
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
-        os.path.dirname(os.path.abspath(__file__)), "..", "squigulator_b200", "data", "ztable_v1.bin")
+        os.path.dirname(os.path.abspath(__file__)), "..", "squigulator_b200", "data", "ztable_v2.bin")
     z1, z2 = build()
     assert np.all(np.diff(z1) > 0) and np.all(np.diff(z2) > 0)
     os.makedirs(os.path.dirname(out), exist_ok=True)
+    z1h = z1.astype(np.float16)
+    assert np.all(np.diff(z1h.astype(np.float32)) >= 0) and np.all(np.isfinite(z1h))
+    z16 = np.concatenate([z1h, -z1h])  # index = 16-bit uniform h: bit 15 is the sign
     with open(out, "wb") as f:
-        f.write(z1.astype("<f4").tobytes())
+        f.write(z16.astype("<f2").tobytes())
         f.write(z2.astype("<f4").tobytes())
+    vh = body_h = (z1h[:N1 - TAIL_CELLS].astype(np.float64) ** 2).sum() / N1 + (z2.astype(np.float64) ** 2).sum() / (N1 * SUB)
+    print(f"variance of the shipped law (fp16 body + fp32 tail) = {vh:.9f}; tail threshold fp16(Z1[{N1 - TAIL_CELLS}]) = {float(z1h[N1 - TAIL_CELLS])!r}")
     v1 = (z1.astype(np.float64) ** 2).mean()
     # exact variance of the two-level law: body cells + refined tail cells
     body = (z1[:N1 - TAIL_CELLS].astype(np.float64) ** 2).sum() / N1

@@ -25,7 +25,7 @@
 #include "../../include/sqg.h"
 #include "sqg_kernels.cuh"
 
-extern "C" const float sqg_ztable_blob[];  // Z1 ++ Z2, embedded from data/ztable_v1.bin (ztable_blob.S)
+extern "C" const unsigned char sqg_ztable_blob[];  // Z16 (binary16) ++ Z2 (binary32), embedded from data/ztable_v2.bin (ztable_blob.S)
 
 namespace {
 
@@ -157,7 +157,7 @@ struct sqg_ctx {
     int num_sms = 0;
     std::string err;
     DevBuf<float2> d_model;
-    DevBuf<float> d_z;  // Z1 ++ Z2
+    DevBuf<unsigned char> d_z;  // Z16 ++ Z2
     GenParams base;     // configuration-derived part of the kernel parameters
     bool noisy = false, rand_dwell = false, meth = false, rev = false, prefix = false;
     int model_in_smem = 0;
@@ -349,8 +349,7 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
     const GenParams p = slot_params(ctx, s);
     CU(cudaMemsetAsync(s.d_meta.p, 0, 4 * sizeof(int64_t), s.stream));
     if (ctx->rand_dwell) {
-        const int grid = (int)std::min<int64_t>(s.n_tiles, (int64_t)ctx->num_sms * 8);
-        dwell_sum_kernel<<<grid, K1_THREADS, 0, s.stream>>>(p);
+        dwell_sum_kernel<<<(int)s.n_tiles, K1_THREADS, 0, s.stream>>>(p);
         ctx->launches++;
     }
     const int g2 = (int)((s.n_reads + 255) / 256);
@@ -378,7 +377,7 @@ int slot_size_arena(sqg_ctx *ctx, Slot &s) {
 int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
-    const int grid = (int)std::min<int64_t>(s.n_tiles, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
+    const int grid = (int)std::min<int64_t>((s.n_tiles + GROUPS - 1) / GROUPS, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
     if (before) CU(cudaEventRecord(before, s.stream));
     void *args[] = {(void *)&p};
@@ -496,7 +495,7 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
     b.digitisation = pr.digitisation; b.range = pr.range; b.scale = pr.digitisation / pr.range;
     b.offset_mean = pr.offset_mean; b.offset_std = pr.offset_std;
     b.median_mean = pr.median_before_mean; b.median_std = pr.median_before_std;
-    b.dwell_mean = pr.dwell_mean; b.dwell_std = pr.dwell_std;
+    b.dwell_mean = (float)pr.dwell_mean; b.dwell_std = (float)pr.dwell_std;
     b.sps_fixed = (int32_t)pr.dwell_mean;
     b.ideal = ideal ? 1 : 0;
     b.amp_noise = cfg->amp_noise;
@@ -514,12 +513,19 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
         }
     }
     if (ctx->rand_dwell) {
-        const double mx = std::floor(pr.dwell_mean + (double)Z_MAX * pr.dwell_std + 0.5) + 1.0;
-        if (!(mx < 8000.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 5.72*dwell_std too large for one tile");
+        // largest possible dwell: |z| <= Z_MAX, folded values included
+        const double mx = std::floor((double)b.dwell_mean + (double)Z_MAX * (double)b.dwell_std + 0.5) + 2.0;
+        if (!(mx < 4000.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 5.72*dwell_std too large for one tile");
         int T = (int)((MAP_CAP * 8 - 16) / (int)mx) & ~7;
         b.T = std::max(8, std::min(T, MAX_T));
     } else {
-        b.T = MAX_T;
+        // n / sps == umulhi(n, magic) needs n * sps < 2^32 for every tile sample n < T * sps
+        const uint64_t sps = (uint64_t)b.sps_fixed;
+        if (sps > 20000) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
+        uint64_t T = std::min<uint64_t>(MAX_T, (0xFFFFFFFFull / (sps * sps)) & ~7ull);
+        if (T < 8) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
+        b.T = (int32_t)T;
+        b.sps_magic = sps == 1 ? 0u : (uint32_t)(0x100000000ull / sps) + 1u;  // sps == 1 is special-cased in div_sps()
     }
     return SQG_OK;
 }
@@ -539,16 +545,17 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     CU(ctx->d_model.ensure(n));
     if (h_model) CU(cudaMemcpy(ctx->d_model.p, h_model, n * sizeof(float2), cudaMemcpyHostToDevice));
     else CU(cudaMemcpy(ctx->d_model.p, d_model_in, n * sizeof(float2), cudaMemcpyDeviceToDevice));
-    CU(ctx->d_z.ensure(Z1_N + 16 * Z2_SUB));
-    CU(cudaMemcpy(ctx->d_z.p, sqg_ztable_blob, (Z1_N + 16 * Z2_SUB) * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t zbytes = (size_t)Z16_N * 2 + 16 * Z2_SUB * sizeof(float);
+    CU(ctx->d_z.ensure(zbytes));
+    CU(cudaMemcpy(ctx->d_z.p, sqg_ztable_blob, zbytes, cudaMemcpyHostToDevice));
     ctx->base.model = ctx->d_model.p;
-    ctx->base.z1 = ctx->d_z.p;
-    ctx->base.z2 = ctx->d_z.p + Z1_N;
+    ctx->base.z16 = reinterpret_cast<const __half *>(ctx->d_z.p);
+    ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z16_N * 2);
 
     // shared-memory plan of the signal kernel: tile state + quantile table (+ the pore model when it is small:
     // R9 6-mer = 32 KB, R9 RNA 5-mer = 8 KB)
     const bool use_z = ctx->noisy || ctx->rand_dwell;
-    size_t smem = ((sizeof(TileSmem) + 127) & ~(size_t)127) + (use_z ? Z1_N * 4 : 0);
+    size_t smem = ((sizeof(CtaShared) + 127) & ~(size_t)127) + (use_z ? (size_t)Z16_N * 2 : 0);
     ctx->model_in_smem = (!ctx->meth && n <= 4096) ? 1 : 0;
     if (ctx->model_in_smem) smem += n * sizeof(float2);
     ctx->base.model_in_smem = ctx->model_in_smem;

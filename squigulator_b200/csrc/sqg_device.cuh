@@ -5,6 +5,7 @@
 // Philox mode is specified in DESIGN.md ("Philox mode"); the test suite holds an independent CPU restatement.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace sqg {
@@ -28,10 +29,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // counter word 3: which family of draws (DESIGN.md "Philox mode")
 enum : uint32_t { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
 
-constexpr int Z1_N = 32768;           // half-normal cells of probability 2^-16
+constexpr int Z16_N = 65536;          // Z16[h]: bit 15 of h = sign, bits 0-14 = half-normal cell of probability 2^-16
 constexpr int Z_TAIL_FIRST = 32752;   // the 16 outermost cells are refined ...
-constexpr int Z2_SUB = 1024;          // ... into 1024 sub-cells each
+constexpr int Z2_SUB = 1024;          // ... into 1024 sub-cells each (Z2, float32)
 constexpr float Z_MAX = 5.7152314f;   // largest table entry (bounds the dwell per k-mer)
+constexpr float Z_TAIL_THR = 3.49609375f;  // fp16(Z1[32752]): |z| >= this <=> possibly a tail cell
 
 struct RngKey {
     uint32_t k0, k1;       // Philox key = seed
@@ -39,20 +41,19 @@ struct RngKey {
 };
 
 // rare path of z16: 10 fresh bits pick the sub-cell
-__device__ __noinline__ float z16_tail(const float *__restrict__ z2g, uint32_t cell, uint32_t c0, RngKey key,
+__device__ __noinline__ float z16_tail(const float *__restrict__ z2g, uint32_t h, uint32_t c0, RngKey key,
                                        uint32_t stream) {
     const uint4 w = philox4x32_10(c0, key.r_lo, key.r_hi, stream, key.k0, key.k1);
-    return __ldg(z2g + (cell - Z_TAIL_FIRST) * Z2_SUB + (w.x & (Z2_SUB - 1)));
+    const float z = __ldg(z2g + ((h & 0x7FFFu) - Z_TAIL_FIRST) * Z2_SUB + (w.x & (Z2_SUB - 1)));
+    return (h & 0x8000u) ? -z : z;
 }
 
-// 16-bit uniform -> N(0,1): sign bit + 15-bit index into the conditional-RMS quantile table
-// (z1 may point to shared or global memory)
-__device__ __forceinline__ float z16(const float *__restrict__ z1, const float *__restrict__ z2g, uint32_t h,
+// 16-bit uniform -> N(0,1): one lookup in the signed binary16 quantile table (global or shared memory)
+__device__ __forceinline__ float z16(const __half *__restrict__ z16t, const float *__restrict__ z2g, uint32_t h,
                                      uint32_t tail_c0, RngKey key, uint32_t tail_stream) {
-    const uint32_t i = h & 0x7FFFu;
-    float z = z1[i];
-    if (__builtin_expect(i >= Z_TAIL_FIRST, 0)) z = z16_tail(z2g, i, tail_c0, key, tail_stream);
-    return __uint_as_float(__float_as_uint(z) ^ ((h & 0x8000u) << 16));
+    float z = __half2float(z16t[h]);
+    if (__builtin_expect((h & 0x7FFFu) >= Z_TAIL_FIRST, 0)) z = z16_tail(z2g, h, tail_c0, key, tail_stream);
+    return z;
 }
 
 // ---- base -> digit (src/seq.h:14-28 and :45-60).  256-entry table: low nibble = base-4 rank with the
@@ -80,10 +81,10 @@ __host__ __device__ inline uint8_t base_code(int c) {
 __device__ __forceinline__ uint32_t to_i16_bits(double v) { return (uint32_t)__double2int_rz(v) & 0xFFFFu; }
 __device__ __forceinline__ uint32_t to_i16_bits(float v) { return (uint32_t)__float2int_rz(v) & 0xFFFFu; }
 
-// dwell of one k-mer from a table normal (src/gensig.c:255-256): round half away, fold below 1
-__device__ __forceinline__ int dwell_from_z(float z, double dwell_mean, double dwell_std) {
-    const double x = __dadd_rn(__dmul_rn((double)z, dwell_std), dwell_mean);
-    int d = (int)round(x);
+// dwell of one k-mer from a table normal (src/gensig.c:255-256): Philox mode rounds the single-precision
+// FMA to nearest (ties to even) and folds values below 1 exactly like the reference
+__device__ __forceinline__ int dwell_from_z(float z, float dwell_mean, float dwell_std) {
+    const int d = __float2int_rn(fmaf(z, dwell_std, dwell_mean));
     return d < 1 ? -d + 1 : d;
 }
 

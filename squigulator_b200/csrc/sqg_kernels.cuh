@@ -2,7 +2,7 @@
 //
 // Work decomposition (DESIGN.md "Kernels"):
 //   a read is 1-2 SEGMENTS (the 2nd only for the RNA stall of --prefix, src/genread.c:88-89);
-//   a segment is cut into TILES of T consecutive k-mers; a tile is what one CTA turns into samples.
+//   a segment is cut into TILES of T consecutive k-mers; a tile is what one thread group turns into samples.
 //
 //   K1 dwell_sum_kernel    per tile: draw the T dwells (Philox), sum them              -> tile_sum
 //   K2 read_plan_kernel    per read: exclusive scan of its tile sums, per-read draws    -> tile_base, siglen, offset, median_before
@@ -41,7 +41,7 @@ struct GenParams {
     const SegDesc *segs;
     const ReadDesc *reads;
     const float2 *model;  // (level_mean, level_stdv) by rank
-    const float *z1;      // Z1[32768]
+    const __half *z16;    // Z16[65536]
     const float *z2;      // Z2[16*1024]
     // plan (written by K1-K3, read by K4)
     int32_t *tile_seg;
@@ -66,9 +66,10 @@ struct GenParams {
     // profile (src/sq.h:47-58) and options
     double digitisation, range, scale;  // scale = digitisation/range
     double offset_mean, offset_std, median_mean, median_std;
-    double dwell_mean, dwell_std;
-    int32_t sps_fixed;  // (int)dwell_mean
-    int32_t ideal;      // SQ_IDEAL: per-read draws replaced by the means
+    float dwell_mean, dwell_std;
+    int32_t sps_fixed;    // fixed-dwell modes: samples per k-mer
+    uint32_t sps_magic;   // floor(2^32/sps_fixed)+1: n/sps_fixed == umulhi(n, magic) for n*sps_fixed < 2^32
+    int32_t ideal;        // SQ_IDEAL: per-read draws replaced by the means
     float amp_noise;
     uint32_t key0, key1;
     int64_t first_read;
@@ -76,10 +77,12 @@ struct GenParams {
     int32_t shift_val;  // (int16)(30*digitisation/range)
 };
 
-constexpr int K1_THREADS = 256;
-constexpr int K4_THREADS = 512;
-constexpr int MAX_T = 2048;
-constexpr int MAP_CAP = 8192;  // 8-sample chunks per tile the chunk->k-mer map can hold
+constexpr int K1_THREADS = 128;
+constexpr int GROUPS = 2;    // independent thread groups per CTA: own tile state, own named barrier
+constexpr int GT = 384;      // threads per group
+constexpr int K4_THREADS = GROUPS * GT;
+constexpr int MAX_T = 1024;  // k-mers per tile
+constexpr int MAP_CAP = 4096;  // 8-sample chunks per tile (random dwell)
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -89,17 +92,14 @@ __device__ __forceinline__ RngKey make_key(const GenParams &p, int read_local) {
     return RngKey{p.key0, p.key1, (uint32_t)r, (uint32_t)(r >> 32)};
 }
 
-// the 8 dwells of k-mer block `blk` (k-mers 8*blk .. 8*blk+7 of the read's draw index space)
-__device__ __forceinline__ void draw_dwell8(const GenParams &p, const float *__restrict__ z1, RngKey key, uint32_t blk,
-                                            int d[8]) {
-    const uint4 w = philox4x32_10(blk, key.r_lo, key.r_hi, ST_DWELL, key.k0, key.k1);
-    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t h = (j & 1) ? (ww[j >> 1] >> 16) : (ww[j >> 1] & 0xFFFFu);
-        const float z = z16(z1, p.z2, h, blk * 8 + j, key, ST_DWELL_TAIL);
-        d[j] = dwell_from_z(z, p.dwell_mean, p.dwell_std);
-    }
+__device__ __forceinline__ uint32_t halfword(const uint4 &w, int j) {  // j in 0..7, compile-time after unrolling
+    const uint32_t x = (j >> 1) == 0 ? w.x : (j >> 1) == 1 ? w.y : (j >> 1) == 2 ? w.z : w.w;
+    return (j & 1) ? (x >> 16) : (x & 0xFFFFu);
+}
+
+// n / sps_fixed for tile-local sample numbers (exact: see GenParams::sps_magic)
+__device__ __forceinline__ uint32_t div_sps(const GenParams &p, uint32_t n) {
+    return p.sps_fixed == 1 ? n : __umulhi(n, p.sps_magic);
 }
 
 __device__ __forceinline__ int find_seg(const SegDesc *__restrict__ segs, int n_segs, int tile) {
@@ -112,38 +112,40 @@ __device__ __forceinline__ int find_seg(const SegDesc *__restrict__ segs, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: per-tile sum of dwells (random-dwell modes only)
+// K1: per-tile sum of dwells (random-dwell modes only).  One CTA per tile, one thread per Philox block of 8 k-mers.
 __global__ void __launch_bounds__(K1_THREADS) dwell_sum_kernel(const __grid_constant__ GenParams p) {
     __shared__ int s_seg;
     __shared__ uint32_t s_part[K1_THREADS / 32];
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) s_seg = find_seg(p.segs, p.n_segs, tile);
-        __syncthreads();
-        const int si = s_seg;
-        const SegDesc seg = p.segs[si];
-        const int kstart = (tile - seg.tile0) * p.T;
-        const int nk_tile = min(p.T, seg.nk - kstart);
-        const RngKey key = make_key(p, seg.read);
-        uint32_t sum = 0;
-        for (int g = threadIdx.x; g * 8 < nk_tile; g += K1_THREADS) {
-            int d[8];
-            draw_dwell8(p, p.z1, key, (uint32_t)((seg.k0_rng + kstart) >> 3) + g, d);
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) s_seg = find_seg(p.segs, p.n_segs, tile);
+    __syncthreads();
+    const int si = s_seg;
+    const SegDesc seg = p.segs[si];
+    const int kstart = (tile - seg.tile0) * p.T;
+    const int nk_tile = min(p.T, seg.nk - kstart);
+    const RngKey key = make_key(p, seg.read);
+    uint32_t sum = 0;
+    const int g = threadIdx.x;
+    if (g * 8 < nk_tile) {
+        const uint32_t blk = (uint32_t)((seg.k0_rng + kstart) >> 3) + g;
+        const uint4 w = philox4x32_10(blk, key.r_lo, key.r_hi, ST_DWELL, key.k0, key.k1);
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (g * 8 + j < nk_tile) sum += (uint32_t)d[j];
+        for (int j = 0; j < 8; j++) {
+            const float z = z16(p.z16, p.z2, halfword(w, j), blk * 8 + j, key, ST_DWELL_TAIL);
+            const int d = dwell_from_z(z, p.dwell_mean, p.dwell_std);
+            if (g * 8 + j < nk_tile) sum += (uint32_t)d;
         }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
 #pragma unroll
-            for (int w = 0; w < K1_THREADS / 32; w++) t += s_part[w];
-            p.tile_sum[tile] = t;
-            p.tile_seg[tile] = si;
-        }
-        __syncthreads();
+        for (int w = 0; w < K1_THREADS / 32; w++) t += s_part[w];
+        p.tile_sum[tile] = t;
+        p.tile_seg[tile] = si;
     }
 }
 
@@ -189,8 +191,8 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
         double z[2];
 #pragma unroll
         for (int d = 0; d < 2; d++) {
-            const float za = z16(p.z1, p.z2, ww[d] & 0xFFFFu, 2 * d, key, ST_READ_TAIL);
-            const float zb = z16(p.z1, p.z2, ww[d] >> 16, 2 * d + 1, key, ST_READ_TAIL);
+            const float za = z16(p.z16, p.z2, ww[d] & 0xFFFFu, 2 * d, key, ST_READ_TAIL);
+            const float zb = z16(p.z16, p.z2, ww[d] >> 16, 2 * d + 1, key, ST_READ_TAIL);
             z[d] = __dadd_rn(__dmul_rn((double)za, 0.8), __dmul_rn((double)zb, 0.6));
         }
         off = __dadd_rn(__dmul_rn(z[0], p.offset_std), p.offset_mean);
@@ -238,7 +240,6 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
         p.read_sigoff[r] = (int64_t)base;
         base += ((uint64_t)p.read_siglen[r] + 63) & ~63ull;
     }
-    // sum of raw lengths: warp + atomics
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, o);
     if (tid == 0) p.meta[1] = 0;
@@ -250,36 +251,55 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // K4: the signal kernel.
 
-struct __align__(16) TileSmem {
-    uint32_t off[MAX_T + 8];      // tile-relative first sample of each k-mer; off[nk] = S
-    float2 par[MAX_T];            // NOISY: (A', B') ; else (unused, int16 value bits)
-    uint16_t map[MAP_CAP];        // chunk -> first k-mer (random dwell only)
-    uint8_t digit[MAX_T + 16];    // base digits of the tile's window
-    uint8_t lut[256];
-    uint32_t warp_sum[K4_THREADS / 32];
+struct __align__(16) TileState {
+    uint32_t off[MAX_T + 8];       // tile-relative first sample of each k-mer; off[nk] = S       (random dwell)
+    float2 par[MAX_T];             // NOISY: (A', B'); else (0, int16 value bits)
+    uint16_t map[MAP_CAP];         // chunk -> k-mer of its first sample                           (random dwell)
+    uint32_t bmap[MAP_CAP / 4];    // byte w: bit b set <=> a k-mer starts at sample b of chunk w   (random dwell)
+    uint8_t digit[MAX_T + 16];     // base digits of the tile's window
+    uint32_t warp_sum[GT / 32];
     uint32_t S;
-    alignas(8) unsigned long long mbar;
+    uint32_t pad[3];
 };
+
+struct __align__(16) CtaShared {
+    TileState ts[GROUPS];
+    uint4 lut[256];     // boundary mask -> byte offsets (8 * k-mers passed) of the 8 samples, 16 bit each
+    uint8_t code[256];  // base -> digits
+    unsigned long long mbar;
+    uint32_t pad[2];
+};
+
+// ---- raw shared-memory access by 32-bit shared address (lets ptxas use LDS [R+UR+imm]) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_half(uint32_t addr) {
+    unsigned short h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+    return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory");
+}
 
 // TMA bulk copy global -> shared (1-D), completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(mbar);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
-                 "l"(gsrc), "r"(bytes), "r"(b)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
                  : "memory");
 }
 __device__ __forceinline__ void mbar_init(unsigned long long *mbar, uint32_t count) {
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(mbar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, uint32_t bytes) {
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(mbar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t phase) {
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(mbar);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -288,83 +308,158 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t pha
         "@p bra WAIT_DONE_%=;\n"
         "bra WAIT_LOOP_%=;\n"
         "WAIT_DONE_%=:\n"
-        "}\n" ::"r"(b),
+        "}\n" ::"r"(smem_u32(mbar)),
         "r"(phase)
         : "memory");
 }
 
-// dynamic shared memory: [TileSmem][z1: 128 KB if USE_Z][model: num_kmer*8 B if model_in_smem]
+// Everything phase B needs to know about the tile
+struct TileCtx {
+    uint32_t S;    // samples in the tile
+    uint32_t ph;   // chunk w covers tile samples [8w-ph, 8w-ph+8)
+    uint32_t B;    // first logical sample of the tile within the read
+    uint32_t L;    // samples in the read
+    int16_t *out;  // start of the read in the signal arena
+    RngKey key;
+};
+
+// Generic (slow) chunk: partial chunks at the tile edges.  Walks the k-mers sample by sample.
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __noinline__ void slow_chunk(const GenParams &p, const TileState &ts, const __half *__restrict__ z16s,
+                                        const TileCtx c, uint32_t w) {
+    const int s0 = (int)(8 * w) - (int)c.ph;
+    const uint32_t q0 = REV ? (c.L - c.B - (uint32_t)(s0 + 8)) : (c.B + (uint32_t)s0);
+    const int sc = max(s0, 0);
+    int k;
+    uint32_t nxt;
+    if (RAND_DWELL) {
+        k = ts.map[w];
+        nxt = ts.off[k + 1];
+    } else {
+        k = (int)div_sps(p, (uint32_t)sc);
+        nxt = (uint32_t)(k + 1) * (uint32_t)p.sps_fixed;
+    }
+    uint4 rw = make_uint4(0, 0, 0, 0);
+    if (NOISY) rw = philox4x32_10(q0 >> 3, c.key.r_lo, c.key.r_hi, ST_AMP, c.key.k0, c.key.k1);
+    for (int j = 0; j < 8; j++) {
+        const int s = s0 + j;
+        const int e = REV ? 7 - j : j;
+        if (s < 0 || (uint32_t)s >= c.S) continue;
+        while ((uint32_t)s >= nxt) {
+            k++;
+            nxt = RAND_DWELL ? ts.off[k + 1] : nxt + (uint32_t)p.sps_fixed;
+        }
+        const float2 ab = ts.par[k];
+        uint32_t bits;
+        if (NOISY) {
+            const uint32_t x = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
+            const uint32_t h = (e & 1) ? (x >> 16) : (x & 0xFFFFu);
+            const float z = z16(z16s, p.z2, h, q0 + e, c.key, ST_AMP_TAIL);
+            bits = to_i16_bits(fmaf(z, ab.x, ab.y));
+        } else {
+            bits = __float_as_uint(ab.y);
+        }
+        c.out[q0 + e] = (int16_t)bits;
+    }
+}
+
+// dynamic shared memory: [CtaShared][Z16: 128 KB if USE_Z][model: num_kmer*8 B if model_in_smem]
 template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
 __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
     constexpr bool USE_Z = NOISY || RAND_DWELL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileSmem &ts = *reinterpret_cast<TileSmem *>(smem_raw);
-    float *z1s = reinterpret_cast<float *>(smem_raw + ((sizeof(TileSmem) + 127) & ~127u));
-    float2 *models = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(z1s) + (USE_Z ? Z1_N * 4 : 0));
+    CtaShared &cs = *reinterpret_cast<CtaShared *>(smem_raw);
+    __half *z16s = reinterpret_cast<__half *>(smem_raw + ((sizeof(CtaShared) + 127) & ~127u));
+    float2 *models = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(z16s) + (USE_Z ? Z16_N * 2 : 0));
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int group = tid / GT;
+    const int gtid = tid - group * GT;
+    const int lane = tid & 31, gwarp = gtid >> 5;
+    TileState &ts = cs.ts[group];
 
     // ---- one-time staging: quantile table and (small) pore model by TMA bulk copies ----
-    if (tid == 0) mbar_init(&ts.mbar, 1);
-    for (int i = tid; i < 256; i += K4_THREADS) ts.lut[i] = base_code(i);
+    if (tid == 0) mbar_init(&cs.mbar, 1);
+    for (int i = tid; i < 256; i += K4_THREADS) {
+        cs.code[i] = base_code(i);
+        uint32_t f[8], cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j >= 1 && ((i >> j) & 1)) cnt++;
+            f[j] = cnt * 8;
+        }
+        cs.lut[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+    }
     __syncthreads();
     if (tid == 0) {
         uint32_t bytes = 0;
-        if (USE_Z) bytes += Z1_N * 4;
+        if (USE_Z) bytes += Z16_N * 2;
         if (p.model_in_smem) bytes += p.num_kmer * 8;
         if (bytes) {
-            mbar_expect_tx(&ts.mbar, bytes);
+            mbar_expect_tx(&cs.mbar, bytes);
             if (USE_Z) {
-                // <= 64 KB per bulk copy keeps each request modest
-                tma_load_1d(z1s, p.z1, Z1_N * 2, &ts.mbar);
-                tma_load_1d(z1s + Z1_N / 2, p.z1 + Z1_N / 2, Z1_N * 2, &ts.mbar);
+                tma_load_1d(z16s, p.z16, Z16_N, &cs.mbar);  // two 64 KB bulk copies
+                tma_load_1d(z16s + Z16_N / 2, p.z16 + Z16_N / 2, Z16_N, &cs.mbar);
             }
-            if (p.model_in_smem) tma_load_1d(models, p.model, p.num_kmer * 8, &ts.mbar);
+            if (p.model_in_smem) tma_load_1d(models, p.model, p.num_kmer * 8, &cs.mbar);
         }
     }
-    if (USE_Z || p.model_in_smem) mbar_wait(&ts.mbar, 0);
+    if (USE_Z || p.model_in_smem) mbar_wait(&cs.mbar, 0);
     const float2 *__restrict__ model = p.model_in_smem ? models : p.model;
+    const uint32_t zbase = smem_u32(z16s);
+    const uint32_t par_addr = smem_u32(ts.par);  // < 64 KB: the tile states lead the shared-memory layout
+    if (par_addr + (MAX_T + 8) * 8 >= 0x10000u) __trap();
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x * GROUPS + group; tile < p.n_tiles; tile += gridDim.x * GROUPS) {
         const int si = p.tile_seg[tile];
         const SegDesc seg = p.segs[si];
         const int kstart = (tile - seg.tile0) * p.T;
         const int nk_tile = min(p.T, seg.nk - kstart);
-        const RngKey key = make_key(p, seg.read);
-        const uint32_t B = p.tile_base[tile];     // first logical sample of the tile within the read
-        const uint32_t L = p.read_siglen[seg.read];
+        TileCtx c;
+        c.key = make_key(p, seg.read);
+        c.B = p.tile_base[tile];  // first logical sample of the tile within the read
+        c.L = p.read_siglen[seg.read];
+        c.out = p.sig + p.read_sigoff[seg.read];
+        // chunk w covers tile samples [8w-ph, 8w-ph+8): chunks are aligned in the EMITTED signal
+        c.ph = REV ? ((c.B - c.L) & 7u) : (c.B & 7u);
         const double offset = p.read_offset[seg.read];
-        int16_t *__restrict__ out = p.sig + p.read_sigoff[seg.read];
 
-        // ---- phase A0: digits of the tile's base window ----
+        // ---- phase A0: digits of the tile's base window; clear the boundary bitmap ----
         const int nb = nk_tile + p.k - 1;
-        for (int i = tid; i < nb; i += K4_THREADS) {
+        for (int i = gtid; i < nb; i += GT) {
             const int pos = kstart + i;
-            const uint8_t c = pos < seg.len_a ? p.bases[seg.off_a + pos] : p.bases[seg.off_b + (pos - seg.len_a)];
-            const uint8_t code = ts.lut[c];
+            const uint8_t ch = pos < seg.len_a ? p.bases[seg.off_a + pos] : p.bases[seg.off_b + (pos - seg.len_a)];
+            const uint8_t code = cs.code[ch];
             ts.digit[i] = METH ? (code >> 4) : (code & 3);
         }
-        __syncthreads();
+        if (RAND_DWELL)
+            for (int i = gtid; i < MAP_CAP / 16; i += GT) reinterpret_cast<uint4 *>(ts.bmap)[i] = make_uint4(0, 0, 0, 0);
+        group_sync(group);
 
-        // ---- phase A1: 8 k-mers per thread: rank, model lookup, dwell, parameters ----
-        const int g = tid;  // group index; groups beyond the tile idle (T/8 <= 256 < K4_THREADS)
-        const bool active = g * 8 < nk_tile;
-        int d[8];
+        // ---- phase A1: 4 k-mers per thread: rank, model lookup, dwell, parameters ----
+        const int m0 = gtid * 4;  // first k-mer of this thread within the tile (T/4 <= 256 <= GT)
+        const bool active = m0 < nk_tile;
+        int d[4] = {0, 0, 0, 0};
         uint32_t local = 0;
-        float2 pr[8];
+        float2 pr[4];
         if (active) {
             if (RAND_DWELL) {
-                draw_dwell8(p, z1s, key, (uint32_t)((seg.k0_rng + kstart) >> 3) + g, d);
+                const uint32_t kidx = (uint32_t)(seg.k0_rng + kstart + m0);  // draw index of the first k-mer (multiple of 4)
+                const uint4 w = philox4x32_10(kidx >> 3, c.key.r_lo, c.key.r_hi, ST_DWELL, c.key.k0, c.key.k1);
+                const uint32_t wa = (kidx & 4) ? w.z : w.x, wb = (kidx & 4) ? w.w : w.y;
+                const uint32_t hh[4] = {wa & 0xFFFFu, wa >> 16, wb & 0xFFFFu, wb >> 16};
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    d[j] = dwell_from_z(z16(z16s, p.z2, hh[j], kidx + j, c.key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; j++) d[j] = p.sps_fixed;
+                for (int j = 0; j < 4; j++) d[j] = p.sps_fixed;
             }
             uint32_t rank = 0;
-            const uint8_t *dg = ts.digit + g * 8;
+            const uint8_t *dg = ts.digit + m0;
             for (int i = 0; i < p.k - 1; i++) rank = METH ? rank * 5 + dg[i] : (rank << 2) | dg[i];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool valid = g * 8 + j < nk_tile;
+            for (int j = 0; j < 4; j++) {
+                const bool valid = m0 + j < nk_tile;
                 if (!valid) d[j] = 0;
                 const uint32_t dn = valid ? dg[p.k - 1 + j] : 0;
                 // src/seq.h:31-42 / :62-74, rolling: drop the leading digit, append the new one
@@ -383,106 +478,122 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
                 local += (uint32_t)d[j];
             }
         }
-        // block-wide exclusive scan of `local`
-        uint32_t inc = local;
+        uint32_t o = 0, S;
+        if (RAND_DWELL) {
+            // group-wide exclusive scan of `local`
+            uint32_t inc = local;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) ts.warp_sum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = lane < K4_THREADS / 32 ? ts.warp_sum[lane] : 0;
-            uint32_t winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += v;
+            for (int sh = 1; sh < 32; sh <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
+                if (lane >= sh) inc += v;
             }
-            if (lane < K4_THREADS / 32) ts.warp_sum[lane] = winc - w;
-            if (lane == 31) ts.S = winc;
-        }
-        __syncthreads();
-        const uint32_t S = ts.S;
-        // phase of the 8-sample chunks relative to the tile: chunk w covers tile samples [8w-ph, 8w-ph+8)
-        const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
-        if (active) {
-            uint32_t o = ts.warp_sum[warp] + inc - local;
+            if (lane == 31) ts.warp_sum[gwarp] = inc;
+            group_sync(group);
+            if (gwarp == 0) {
+                const uint32_t ws = lane < GT / 32 ? ts.warp_sum[lane] : 0;
+                uint32_t winc = ws;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int m = g * 8 + j;
+                for (int sh = 1; sh < 16; sh <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, winc, sh);
+                    if (lane >= sh) winc += v;
+                }
+                if (lane < GT / 32) ts.warp_sum[lane] = winc - ws;
+                if (lane == GT / 32 - 1) ts.S = winc;
+            }
+            group_sync(group);
+            S = ts.S;
+            o = ts.warp_sum[gwarp] + inc - local;
+        } else {
+            S = (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
+            o = (uint32_t)m0 * (uint32_t)p.sps_fixed;
+        }
+        c.S = S;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int m = m0 + j;
                 if (m < nk_tile) {
-                    ts.off[m] = o;
                     ts.par[m] = pr[j];
                     if (RAND_DWELL) {
+                        ts.off[m] = o;
                         // chunks whose first (clipped) sample falls inside this k-mer
-                        uint32_t w0 = m == 0 ? 0u : (o + ph + 7) >> 3;
-                        const uint32_t w1 = (o + (uint32_t)d[j] + ph + 7) >> 3;
+                        uint32_t w0 = m == 0 ? 0u : (o + c.ph + 7) >> 3;
+                        const uint32_t w1 = (o + (uint32_t)d[j] + c.ph + 7) >> 3;
                         for (; w0 < w1; w0++) ts.map[w0] = (uint16_t)m;
+                        const uint32_t pos = o + c.ph;  // boundary bit: this k-mer starts at bit (pos&7) of chunk (pos>>3)
+                        atomicOr(&ts.bmap[pos >> 5], 1u << (pos & 31));
                     }
                     if (p.want_ss) p.ss[p.reads[seg.read].ss_off + seg.k0 + kstart + m] = d[j];
                     o += (uint32_t)d[j];
                 }
             }
-            if ((g + 1) * 8 >= nk_tile) ts.off[nk_tile] = S;
+            if (RAND_DWELL && m0 + 4 >= nk_tile) ts.off[nk_tile] = S;
         }
-        __syncthreads();
+        group_sync(group);
 
         // ---- phase B: samples.  One thread = one 16-byte chunk of the emitted signal. ----
-        const uint32_t nW = (S + ph + 7) >> 3;
-        for (uint32_t w = tid; w < nW; w += K4_THREADS) {
-            const int s0 = (int)(8 * w) - (int)ph;  // first tile sample of the chunk (may be < 0)
-            const uint32_t q0 = REV ? (L - B - (uint32_t)(s0 + 8)) : (B + (uint32_t)s0);  // emitted position, multiple of 8
-            int k;
-            uint32_t nxt;
-            if (RAND_DWELL) {
-                k = ts.map[w];
-                nxt = ts.off[k + 1];
-            } else {
-                const int sc = max(s0, 0);
-                k = sc / p.sps_fixed;
-                nxt = (uint32_t)(k + 1) * (uint32_t)p.sps_fixed;
+        const uint32_t nW = (S + c.ph + 7) >> 3;
+        for (uint32_t w = gtid; w < nW; w += GT) {
+            const int s0 = (int)(8 * w) - (int)c.ph;  // first tile sample of the chunk (may be < 0)
+            if (s0 < 0 || (uint32_t)(s0 + 8) > S) {
+                slow_chunk<NOISY, RAND_DWELL, REV>(p, ts, z16s, c, w);
+                continue;
             }
-            float2 ab = ts.par[k];
-            uint4 r0 = make_uint4(0, 0, 0, 0);
-            if (NOISY) r0 = philox4x32_10(q0 >> 3, key.r_lo, key.r_hi, ST_AMP, key.k0, key.k1);
-            const uint32_t rw[4] = {r0.x, r0.y, r0.z, r0.w};
+            const uint32_t q0 = REV ? (c.L - c.B - (uint32_t)(s0 + 8)) : (c.B + (uint32_t)s0);  // emitted position, multiple of 8
+            // k-mer of the first sample and the boundary mask of the chunk
+            uint32_t k0, bm;
+            if (RAND_DWELL) {
+                k0 = ts.map[w];
+                bm = reinterpret_cast<const uint8_t *>(ts.bmap)[w] & 0xFEu;
+            } else {
+                k0 = div_sps(p, (uint32_t)s0);
+                bm = 0;
+                for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - (uint32_t)s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << b;
+            }
+            const uint4 lu = cs.lut[bm];
+            const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
+            const uint32_t pa[4] = {lu.x + rep, lu.y + rep, lu.z + rep, lu.w + rep};
             uint32_t v[8];
+            if (NOISY) {
+                const uint4 r4 = philox4x32_10(q0 >> 3, c.key.r_lo, c.key.r_hi, ST_AMP, c.key.k0, c.key.k1);
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                float zmax = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int s = s0 + j;
-                const int e = REV ? 7 - j : j;  // slot in the emitted chunk
-                uint32_t bits = 0;
-                if (s >= 0 && (uint32_t)s < S) {
-                    if ((uint32_t)s >= nxt) {
-                        k++;
-                        nxt = RAND_DWELL ? ts.off[k + 1] : nxt + (uint32_t)p.sps_fixed;
-                        ab = ts.par[k];
-                    }
-                    if (NOISY) {
+                for (int j = 0; j < 8; j++) {
+                    const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
+                    const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
+                    const uint32_t h = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
+                    const float z = lds_half(zbase + 2u * h);  // extract + one multiply-add for the address
+                    zmax = fmaxf(zmax, fabsf(z));
+                    v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
+                }
+                if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
+                    // rare: some draw fell into one of the 16 outermost cells -> refine it (10 more bits)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int e = REV ? 7 - j : j;
                         const uint32_t h = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
-                        const float z = z16(z1s, p.z2, h, q0 + e, key, ST_AMP_TAIL);
-                        bits = to_i16_bits(fmaf(z, ab.x, ab.y));
-                    } else {
-                        bits = __float_as_uint(ab.y);
+                        if ((h & 0x7FFFu) >= Z_TAIL_FIRST) {
+                            const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
+                            const float z = z16_tail(p.z2, h, q0 + e, c.key, ST_AMP_TAIL);
+                            v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
+                        }
                     }
                 }
-                v[e] = bits;
-            }
-            if (s0 >= 0 && (uint32_t)(s0 + 8) <= S) {
-                const uint4 pk = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-                __stcs(reinterpret_cast<uint4 *>(out + q0), pk);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const int s = s0 + j;
                     const int e = REV ? 7 - j : j;
-                    if (s >= 0 && (uint32_t)s < S) out[q0 + e] = (int16_t)v[e];
+                    const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
+                    v[e] = __float_as_uint(ab.y);
                 }
             }
+            // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
+            const uint4 pk = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
+                                        __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
+            __stcs(reinterpret_cast<uint4 *>(c.out + q0), pk);
         }
-        __syncthreads();  // tile state is reused by the next tile
+        group_sync(group);  // the tile state is reused by this group's next tile
     }
 }
 

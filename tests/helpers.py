@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-ZTABLE = os.path.join(ROOT, "squigulator_b200", "data", "ztable_v1.bin")
+ZTABLE = os.path.join(ROOT, "squigulator_b200", "data", "ztable_v2.bin")
 
 PROFILE_FIELDS = ["digitisation", "sample_rate", "bps", "range", "offset_mean", "offset_std",
                   "median_before_mean", "median_before_std", "dwell_mean", "dwell_std"]
@@ -54,7 +54,7 @@ def build_oracle():
 def load_oracle():
     lib = C.CDLL(build_oracle())
     lib.sqo_open.restype = C.c_void_p
-    lib.sqo_open.argtypes = [C.POINTER(OracleConfig), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.sqo_open.argtypes = [C.POINTER(OracleConfig), C.POINTER(C.c_float), C.c_void_p]
     lib.sqo_close.argtypes = [C.c_void_p]
     lib.sqo_gen_sig.restype = C.c_int64
     lib.sqo_gen_sig.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int, C.POINTER(C.c_double),
@@ -74,8 +74,8 @@ def load_oracle():
 
 
 def load_ztable():
-    t = np.fromfile(ZTABLE, dtype="<f4")
-    assert t.size == 32768 + 16384
+    t = np.fromfile(ZTABLE, dtype=np.uint8)  # Z16[65536] binary16 ++ Z2[16384] binary32
+    assert t.size == 65536 * 2 + 16384 * 4
     return np.ascontiguousarray(t)
 
 
@@ -96,7 +96,7 @@ class Oracle:
         self._model = np.ascontiguousarray(model, dtype=np.float32)
         assert self._model.size == 2 * num_kmer
         self._zt = ztable
-        zp = ztable.ctypes.data_as(C.POINTER(C.c_float)) if ztable is not None else None
+        zp = ztable.ctypes.data_as(C.c_void_p) if ztable is not None else None
         self.h = lib.sqo_open(C.byref(cfg), self._model.ctypes.data_as(C.POINTER(C.c_float)), zp)
         assert self.h
 
