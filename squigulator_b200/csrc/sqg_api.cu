@@ -197,15 +197,27 @@ int fail(sqg_ctx *ctx, int code, const char *msg) {
 
 typedef void (*k4_fn)(const GenParams);
 
-k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev) {
-#define K4(a, b, c, d) (k4_fn) signal_kernel<a, b, c, d>
-    static const k4_fn tab[16] = {
-        K4(false, false, false, false), K4(false, false, false, true), K4(false, false, true, false), K4(false, false, true, true),
-        K4(false, true, false, false),  K4(false, true, false, true),  K4(false, true, true, false),  K4(false, true, true, true),
-        K4(true, false, false, false),  K4(true, false, false, true),  K4(true, false, true, false),  K4(true, false, true, true),
-        K4(true, true, false, false),   K4(true, true, false, true),   K4(true, true, true, false),   K4(true, true, true, true)};
-#undef K4
-    return tab[(noisy << 3) | (rnd << 2) | (meth << 1) | (int)rev];
+template <int I>
+struct K4Table {
+    static void fill(k4_fn *t) {
+        t[I] = (k4_fn)signal_kernel<(I >> 4) & 1, (I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
+        K4Table<I - 1>::fill(t);
+    }
+};
+template <>
+struct K4Table<-1> {
+    static void fill(k4_fn *) {}
+};
+
+// the 32 instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>
+k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev, bool model_smem) {
+    static k4_fn tab[32];
+    static bool init = false;
+    if (!init) {
+        K4Table<31>::fill(tab);
+        init = true;
+    }
+    return tab[(noisy << 4) | (rnd << 3) | (meth << 2) | (rev << 1) | (int)model_smem];
 }
 
 int slot_init(sqg_ctx *ctx, Slot &s) {
@@ -348,8 +360,11 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
     CU(cudaMemsetAsync(s.d_meta.p, 0, 4 * sizeof(int64_t), s.stream));
+    tile_map_kernel<<<(int)((s.n_segs + 255) / 256), 256, 0, s.stream>>>(p);
+    ctx->launches++;
     if (ctx->rand_dwell) {
-        dwell_sum_kernel<<<(int)s.n_tiles, K1_THREADS, 0, s.stream>>>(p);
+        const int tiles_per_cta = K1_THREADS / 32;
+        dwell_sum_kernel<<<(int)((s.n_tiles + tiles_per_cta - 1) / tiles_per_cta), K1_THREADS, 0, s.stream>>>(p);
         ctx->launches++;
     }
     const int g2 = (int)((s.n_reads + 255) / 256);
@@ -377,8 +392,8 @@ int slot_size_arena(sqg_ctx *ctx, Slot &s) {
 int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
-    const int grid = (int)std::min<int64_t>((s.n_tiles + GROUPS - 1) / GROUPS, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    const int grid = (int)std::min<int64_t>((s.n_tiles + NTEAM - 1) / NTEAM, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
     if (before) CU(cudaEventRecord(before, s.stream));
     void *args[] = {(void *)&p};
     CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(K4_THREADS), args, ctx->k4_smem, s.stream));
@@ -515,17 +530,21 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
     if (ctx->rand_dwell) {
         // largest possible dwell: |z| <= Z_MAX, folded values included
         const double mx = std::floor((double)b.dwell_mean + (double)Z_MAX * (double)b.dwell_std + 0.5) + 2.0;
-        if (!(mx < 4000.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 5.72*dwell_std too large for one tile");
-        int T = (int)((MAP_CAP * 8 - 16) / (int)mx) & ~7;
-        b.T = std::max(8, std::min(T, MAX_T));
+        if (!(mx < 1200.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 5.72*dwell_std too large for one tile");
+        int T = (int)((MAPC * 8 - 16) / (int)mx) & ~7;
+        b.T = std::max(8, std::min(T, TK));
     } else {
         // n / sps == umulhi(n, magic) needs n * sps < 2^32 for every tile sample n < T * sps
         const uint64_t sps = (uint64_t)b.sps_fixed;
         if (sps > 20000) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
-        uint64_t T = std::min<uint64_t>(MAX_T, (0xFFFFFFFFull / (sps * sps)) & ~7ull);
+        uint64_t T = std::min<uint64_t>(TK, (0xFFFFFFFFull / (sps * sps)) & ~7ull);
         if (T < 8) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
         b.T = (int32_t)T;
         b.sps_magic = sps == 1 ? 0u : (uint32_t)(0x100000000ull / sps) + 1u;  // sps == 1 is special-cased in div_sps()
+    }
+    for (int r = 0; r < 10; r++) {
+        b.rk[2 * r] = b.key0 + (uint32_t)r * 0x9E3779B9u;
+        b.rk[2 * r + 1] = b.key1 + (uint32_t)r * 0xBB67AE85u;
     }
     return SQG_OK;
 }
@@ -555,12 +574,12 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     // shared-memory plan of the signal kernel: tile state + quantile table (+ the pore model when it is small:
     // R9 6-mer = 32 KB, R9 RNA 5-mer = 8 KB)
     const bool use_z = ctx->noisy || ctx->rand_dwell;
-    size_t smem = ((sizeof(CtaShared) + 127) & ~(size_t)127) + (use_z ? (size_t)Z16_N * 2 : 0);
+    size_t smem = ((sizeof(K4Shared) + 127) & ~(size_t)127) + (use_z ? (size_t)Z16_N * 2 : 0);
     ctx->model_in_smem = (!ctx->meth && n <= 4096) ? 1 : 0;
     if (ctx->model_in_smem) smem += n * sizeof(float2);
     ctx->base.model_in_smem = ctx->model_in_smem;
     ctx->k4_smem = smem;
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
     CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, K4_THREADS, smem));

@@ -26,6 +26,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Same function with the ten round keys precomputed on the host (GenParams::rk lives in the constant bank, so
+// the key schedule costs no issue slots inside the sample loop)
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  const uint32_t *__restrict__ rk) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // counter word 3: which family of draws (DESIGN.md "Philox mode")
 enum : uint32_t { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
 

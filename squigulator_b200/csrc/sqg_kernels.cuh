@@ -4,6 +4,7 @@
 //   a read is 1-2 SEGMENTS (the 2nd only for the RNA stall of --prefix, src/genread.c:88-89);
 //   a segment is cut into TILES of T consecutive k-mers; a tile is what one thread group turns into samples.
 //
+//   K0 tile_map_kernel     per segment: tile -> segment                                 -> tile_seg
 //   K1 dwell_sum_kernel    per tile: draw the T dwells (Philox), sum them              -> tile_sum
 //   K2 read_plan_kernel    per read: exclusive scan of its tile sums, per-read draws    -> tile_base, siglen, offset, median_before
 //   K3 read_offsets_kernel one CTA : exclusive scan of the 64-sample-aligned read lengths -> sigoff, totals
@@ -72,17 +73,13 @@ struct GenParams {
     int32_t ideal;        // SQ_IDEAL: per-read draws replaced by the means
     float amp_noise;
     uint32_t key0, key1;
+    uint32_t rk[20];      // the ten Philox round keys (k0 + r*W0, k1 + r*W1), precomputed
     int64_t first_read;
     int32_t want_ss;
     int32_t shift_val;  // (int16)(30*digitisation/range)
 };
 
-constexpr int K1_THREADS = 128;
-constexpr int GROUPS = 2;    // independent thread groups per CTA: own tile state, own named barrier
-constexpr int GT = 384;      // threads per group
-constexpr int K4_THREADS = GROUPS * GT;
-constexpr int MAX_T = 1024;  // k-mers per tile
-constexpr int MAP_CAP = 4096;  // 8-sample chunks per tile (random dwell)
+constexpr int K1_THREADS = 128;  // 4 tiles per CTA, one warp each
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -112,41 +109,37 @@ __device__ __forceinline__ int find_seg(const SegDesc *__restrict__ segs, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: per-tile sum of dwells (random-dwell modes only).  One CTA per tile, one thread per Philox block of 8 k-mers.
+// K0: tile -> segment map (one thread per segment)
+__global__ void __launch_bounds__(256) tile_map_kernel(const __grid_constant__ GenParams p) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n_segs) return;
+    const int t0 = p.segs[s].tile0, nt = (p.segs[s].nk + p.T - 1) / p.T;
+    for (int t = 0; t < nt; t++) p.tile_seg[t0 + t] = s;
+}
+
+// K1: per-tile sum of dwells (random-dwell modes only).  One warp per tile, one lane per Philox block of 8 k-mers.
 __global__ void __launch_bounds__(K1_THREADS) dwell_sum_kernel(const __grid_constant__ GenParams p) {
-    __shared__ int s_seg;
-    __shared__ uint32_t s_part[K1_THREADS / 32];
-    const int tile = blockIdx.x;
-    if (threadIdx.x == 0) s_seg = find_seg(p.segs, p.n_segs, tile);
-    __syncthreads();
-    const int si = s_seg;
-    const SegDesc seg = p.segs[si];
+    const int tile = blockIdx.x * (K1_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tile >= p.n_tiles) return;
+    const SegDesc seg = p.segs[p.tile_seg[tile]];
     const int kstart = (tile - seg.tile0) * p.T;
     const int nk_tile = min(p.T, seg.nk - kstart);
     const RngKey key = make_key(p, seg.read);
     uint32_t sum = 0;
-    const int g = threadIdx.x;
-    if (g * 8 < nk_tile) {
-        const uint32_t blk = (uint32_t)((seg.k0_rng + kstart) >> 3) + g;
-        const uint4 w = philox4x32_10(blk, key.r_lo, key.r_hi, ST_DWELL, key.k0, key.k1);
+    if (lane * 8 < nk_tile) {
+        const uint32_t blk = (uint32_t)((seg.k0_rng + kstart) >> 3) + lane;
+        const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const float z = z16(p.z16, p.z2, halfword(w, j), blk * 8 + j, key, ST_DWELL_TAIL);
             const int d = dwell_from_z(z, p.dwell_mean, p.dwell_std);
-            if (g * 8 + j < nk_tile) sum += (uint32_t)d;
+            if (lane * 8 + j < nk_tile) sum += (uint32_t)d;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-#pragma unroll
-        for (int w = 0; w < K1_THREADS / 32; w++) t += s_part[w];
-        p.tile_sum[tile] = t;
-        p.tile_seg[tile] = si;
-    }
+    if (lane == 0) p.tile_sum[tile] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -169,7 +162,6 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
             } else {
                 sum = (uint32_t)min(p.T, seg.nk - t * p.T) * (uint32_t)p.sps_fixed;
                 p.tile_sum[tile] = sum;
-                p.tile_seg[tile] = s;
             }
             p.tile_base[tile] = (uint32_t)total;
             total += sum;
@@ -250,27 +242,48 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
 
 // ------------------------------------------------------------------------------------------------
 // K4: the signal kernel.
+//
+// A CTA is NTEAM independent TEAMS of (1 producer warp + NCONS consumer warps) that share only the read-only
+// tables in shared memory (quantile table, boundary LUT, base codes, small pore models).  A team works through
+// its own sequence of tiles with a ring of NBUF tile buffers handed over by mbarriers — there is no CTA-wide
+// barrier after the prologue, so k-mer preparation (latency-bound: model gathers, scan) always overlaps sample
+// emission (issue-bound).
+//   producer lane  : 8 consecutive k-mers = one Philox dwell block: digits -> ranks -> (mean,stdv) -> (A',B'),
+//                    8 dwells, warp scan, then the tile buffer: par[], chunk->k-mer map, boundary bitmap
+//   consumer thread: one 16-byte chunk (8 samples) of the emitted signal per iteration: k-mer of the first
+//                    sample from the map, the chunk's boundary byte -> LUT -> the 8 parameter addresses,
+//                    one Philox block -> 8 table normals -> FFMA -> cvt.rzi -> 128-bit store
 
-struct __align__(16) TileState {
-    uint32_t off[MAX_T + 8];       // tile-relative first sample of each k-mer; off[nk] = S       (random dwell)
-    float2 par[MAX_T];             // NOISY: (A', B'); else (0, int16 value bits)
-    uint16_t map[MAP_CAP];         // chunk -> k-mer of its first sample                           (random dwell)
-    uint32_t bmap[MAP_CAP / 4];    // byte w: bit b set <=> a k-mer starts at sample b of chunk w   (random dwell)
-    uint8_t digit[MAX_T + 16];     // base digits of the tile's window
-    uint32_t warp_sum[GT / 32];
-    uint32_t S;
-    uint32_t pad[3];
+constexpr int NTEAM = 6;     // teams per CTA
+constexpr int NCONS = 3;     // consumer warps per team
+constexpr int TEAM_WARPS = 1 + NCONS;
+constexpr int K4_THREADS = NTEAM * TEAM_WARPS * 32;  // 768
+constexpr int NBUF = 2;      // tile buffers per team
+constexpr int TK = 256;      // k-mers per tile (32 lanes x 8)
+constexpr int MAPC = 1280;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8
+constexpr int DIG_BYTES = TK + 32;
+
+struct __align__(16) TileHdr {
+    uint32_t S;      // samples in the tile
+    uint32_t ph;     // chunk w covers tile samples [8w-ph, 8w-ph+8)
+    uint32_t B;      // first logical sample of the tile within the read
+    uint32_t L;      // samples in the read
+    uint32_t r_lo, r_hi;  // global read index (Philox counter words 1,2)
+    uint32_t out_lo, out_hi;  // start of the read in the signal arena
 };
 
-struct __align__(16) CtaShared {
-    TileState ts[GROUPS];
-    uint4 lut[256];     // boundary mask -> byte offsets (8 * k-mers passed) of the 8 samples, 16 bit each
-    uint8_t code[256];  // base -> digits
-    unsigned long long mbar;
-    uint32_t pad[2];
+struct __align__(16) K4Shared {
+    float2 par[NTEAM][NBUF][TK];      // must stay below 64 KB: phase B packs these addresses into 16 bits
+    uint8_t map[NTEAM][NBUF][MAPC];   // chunk -> k-mer (within the tile) of its first sample      (random dwell)
+    uint8_t bmap[NTEAM][NBUF][MAPC];  // byte w: bit b set <=> a k-mer starts at sample b of chunk w (random dwell)
+    TileHdr hdr[NTEAM][NBUF];
+    uint8_t digit[NTEAM][DIG_BYTES];  // producer-private: base digits of the tile's window
+    uint4 lut[256];                   // boundary byte -> 8 x 16-bit byte offsets (8 * k-mers passed)
+    uint8_t code[256];                // base -> digits
+    unsigned long long full[NTEAM][NBUF], empty[NTEAM][NBUF], stage_bar;
 };
 
-// ---- raw shared-memory access by 32-bit shared address (lets ptxas use LDS [R+UR+imm]) ----
+// ---- raw shared-memory access by 32-bit shared address ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float lds_half(uint32_t addr) {
     unsigned short h;
@@ -282,24 +295,23 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void group_sync(int group) {
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GT) : "memory");
-}
 
-// TMA bulk copy global -> shared (1-D), completion on an mbarrier (SASS: UBLKCP)
+// ---- mbarrier / TMA bulk copy (SASS: SYNCS, UBLKCP) ----
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
                  : "memory");
 }
 __device__ __forceinline__ void mbar_init(unsigned long long *mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t phase) {
+__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -309,76 +321,288 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t pha
         "bra WAIT_LOOP_%=;\n"
         "WAIT_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(mbar)),
-        "r"(phase)
+        "r"(parity)
         : "memory");
 }
 
-// Everything phase B needs to know about the tile
-struct TileCtx {
-    uint32_t S;    // samples in the tile
-    uint32_t ph;   // chunk w covers tile samples [8w-ph, 8w-ph+8)
-    uint32_t B;    // first logical sample of the tile within the read
-    uint32_t L;    // samples in the read
-    int16_t *out;  // start of the read in the signal arena
-    RngKey key;
-};
+// ---- consumer side -----------------------------------------------------------------------------------------
 
-// Generic (slow) chunk: partial chunks at the tile edges.  Walks the k-mers sample by sample.
+// Generic (slow) chunk: the clipped chunks at the two ends of a tile.  Walks the boundary bits sample by sample.
 template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __noinline__ void slow_chunk(const GenParams &p, const TileState &ts, const __half *__restrict__ z16s,
-                                        const TileCtx c, uint32_t w) {
-    const int s0 = (int)(8 * w) - (int)c.ph;
-    const uint32_t q0 = REV ? (c.L - c.B - (uint32_t)(s0 + 8)) : (c.B + (uint32_t)s0);
-    const int sc = max(s0, 0);
-    int k;
-    uint32_t nxt;
+__device__ __noinline__ void slow_chunk(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
+                                        const __half *__restrict__ z16s, const TileHdr h, int16_t *out, uint32_t w) {
+    const int s0 = (int)(8 * w) - (int)h.ph;
+    const uint32_t q0 = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);
+    const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
+    const int first = max(s0, 0) - s0;  // first valid slot
+    uint32_t k, nxt = 0;
+    uint32_t bits = 0;
     if (RAND_DWELL) {
-        k = ts.map[w];
-        nxt = ts.off[k + 1];
+        k = map[w];
+        bits = bmap[w];
     } else {
-        k = (int)div_sps(p, (uint32_t)sc);
-        nxt = (uint32_t)(k + 1) * (uint32_t)p.sps_fixed;
+        k = div_sps(p, (uint32_t)max(s0, 0));
+        nxt = (k + 1) * (uint32_t)p.sps_fixed;
     }
     uint4 rw = make_uint4(0, 0, 0, 0);
-    if (NOISY) rw = philox4x32_10(q0 >> 3, c.key.r_lo, c.key.r_hi, ST_AMP, c.key.k0, c.key.k1);
-    for (int j = 0; j < 8; j++) {
+    if (NOISY) rw = philox4x32_10_rk(q0 >> 3, h.r_lo, h.r_hi, ST_AMP, p.rk);
+    for (int j = first; j < 8; j++) {
         const int s = s0 + j;
-        const int e = REV ? 7 - j : j;
-        if (s < 0 || (uint32_t)s >= c.S) continue;
-        while ((uint32_t)s >= nxt) {
+        if ((uint32_t)s >= h.S) break;
+        if (RAND_DWELL) {
+            if (j > first && ((bits >> j) & 1u)) k++;
+        } else if ((uint32_t)s >= nxt) {
             k++;
-            nxt = RAND_DWELL ? ts.off[k + 1] : nxt + (uint32_t)p.sps_fixed;
+            nxt += (uint32_t)p.sps_fixed;
         }
-        const float2 ab = ts.par[k];
-        uint32_t bits;
+        const int e = REV ? 7 - j : j;
+        const float2 ab = par[k];
+        uint32_t v;
         if (NOISY) {
             const uint32_t x = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
-            const uint32_t h = (e & 1) ? (x >> 16) : (x & 0xFFFFu);
-            const float z = z16(z16s, p.z2, h, q0 + e, c.key, ST_AMP_TAIL);
-            bits = to_i16_bits(fmaf(z, ab.x, ab.y));
+            const uint32_t hw = (e & 1) ? (x >> 16) : (x & 0xFFFFu);
+            const float z = z16(z16s, p.z2, hw, q0 + e, key, ST_AMP_TAIL);
+            v = to_i16_bits(fmaf(z, ab.x, ab.y));
         } else {
-            bits = __float_as_uint(ab.y);
+            v = __float_as_uint(ab.y);
         }
-        c.out[q0 + e] = (int16_t)bits;
+        out[q0 + e] = (int16_t)v;
     }
 }
 
-// dynamic shared memory: [CtaShared][Z16: 128 KB if USE_Z][model: num_kmer*8 B if model_in_smem]
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __forceinline__ void consume_tile(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
+                                             const uint4 *lut, const __half *z16s, const TileHdr h, int ctid) {
+    int16_t *out = reinterpret_cast<int16_t *>(((uint64_t)h.out_hi << 32) | h.out_lo);
+    const uint32_t zbase = smem_u32(z16s);
+    const uint32_t par_addr = smem_u32(par);  // < 64 KB by layout
+    const uint32_t nW = (h.S + h.ph + 7) >> 3;
+    for (uint32_t w = ctid; w < nW; w += NCONS * 32) {
+        const int s0 = (int)(8 * w) - (int)h.ph;  // first tile sample of the chunk (may be < 0)
+        if (s0 < 0 || (uint32_t)(s0 + 8) > h.S) {
+            slow_chunk<NOISY, RAND_DWELL, REV>(p, par, map, bmap, z16s, h, out, w);
+            continue;
+        }
+        const uint32_t q0 = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);  // emitted position, multiple of 8
+        uint32_t k0, bm;
+        if (RAND_DWELL) {
+            k0 = map[w];
+            bm = bmap[w] & 0xFEu;
+        } else {
+            k0 = div_sps(p, (uint32_t)s0);
+            bm = 0;
+            for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - (uint32_t)s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << b;
+        }
+        const uint4 lu = lut[bm];
+        const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
+        const uint32_t pa[4] = {lu.x + rep, lu.y + rep, lu.z + rep, lu.w + rep};
+        uint32_t v[8];
+        if (NOISY) {
+            const uint4 r4 = philox4x32_10_rk(q0 >> 3, h.r_lo, h.r_hi, ST_AMP, p.rk);
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+            float zmax = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
+                const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
+                const uint32_t hw = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
+                const float z = lds_half(zbase + 2u * hw);
+                zmax = fmaxf(zmax, fabsf(z));
+                v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
+            }
+            if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
+                // rare: some draw fell into one of the 16 outermost cells -> refine it (10 more bits)
+                const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int e = REV ? 7 - j : j;
+                    const uint32_t hw = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
+                    if ((hw & 0x7FFFu) >= Z_TAIL_FIRST) {
+                        const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
+                        const float z = z16_tail(p.z2, hw, q0 + e, key, ST_AMP_TAIL);
+                        v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = REV ? 7 - j : j;
+                const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
+                v[e] = __float_as_uint(ab.y);
+            }
+        }
+        // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
+        const uint4 pk = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
+                                    __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
+        __stcs(reinterpret_cast<uint4 *>(out + q0), pk);
+    }
+}
+
+// ---- producer side -----------------------------------------------------------------------------------------
+
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
+__device__ __forceinline__ void produce_tile(const GenParams &p, K4Shared &cs, int team, int buf, int tile, int lane,
+                                             const float2 *__restrict__ model, const __half *z16s,
+                                             unsigned long long *empty_bar, uint32_t empty_parity) {
+    const int si = p.tile_seg[tile];
+    const SegDesc seg = p.segs[si];
+    const int kstart = (tile - seg.tile0) * p.T;
+    const int nk_tile = min(p.T, seg.nk - kstart);
+    const RngKey key = make_key(p, seg.read);
+    const uint32_t B = p.tile_base[tile];
+    const uint32_t L = p.read_siglen[seg.read];
+    const double offset = p.read_offset[seg.read];
+    int16_t *out = p.sig + p.read_sigoff[seg.read];
+    const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
+
+    // digits of the tile's base window (coalesced byte loads; the code table folds IUPAC letters, src/seq.h:14-28)
+    uint8_t *dig = cs.digit[team];
+    const int nb = nk_tile + p.k - 1;
+    for (int i = lane; i < nb; i += 32) {
+        const int pos = kstart + i;
+        const uint8_t ch = pos < seg.len_a ? p.bases[seg.off_a + pos] : p.bases[seg.off_b + (pos - seg.len_a)];
+        const uint8_t code = cs.code[ch];
+        dig[i] = METH ? (code >> 4) : (code & 3);
+    }
+    __syncwarp();
+
+    // this lane's 8 k-mers
+    const int m0 = lane * 8;
+    const bool active = m0 < nk_tile;
+    int d[8];
+    float2 pr[8];
+    uint32_t local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) d[j] = 0;
+    if (active) {
+        if (RAND_DWELL) {
+            const uint32_t blk = (uint32_t)((seg.k0_rng + kstart + m0) >> 3);
+            const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                d[j] = dwell_from_z(z16(z16s, p.z2, halfword(w, j), blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = p.sps_fixed;
+        }
+        // 16 digits: k-1 to prime the rank, then one per k-mer (k <= 9)
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(dig + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(dig + m0 + 8);
+        const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
+        uint32_t rank = 0;
+        const int km1 = p.k - 1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i < km1) {
+                const uint32_t dg = (dw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                rank = METH ? rank * 5 + dg : (rank << 2) | dg;
+            }
+        }
+        uint32_t ranks[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            // digit km1 + j: a dynamic byte index into the 16 staged digits
+            const int bi = km1 + j;
+            const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
+            const uint32_t dn = (word >> (8 * (bi & 3))) & 0xFFu;
+            // src/seq.h:31-42 / :62-74, rolling: drop the leading digit, append the new one
+            rank = METH ? (rank % p.kmask) * 5 + dn : ((rank << 2) | dn) & p.kmask;
+            ranks[j] = (m0 + j < nk_tile) ? rank : 0;
+        }
+        float2 mv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) mv[j] = MODEL_SMEM ? model[ranks[j]] : __ldg(&model[ranks[j]]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (m0 + j >= nk_tile) d[j] = 0;
+            if (NOISY) {
+                const float sd = __fmul_rn(mv[j].y, p.amp_noise);  // float product, src/sim.c:249
+                const double a = __dmul_rn((double)sd, p.scale);
+                const double b = __dsub_rn(__dmul_rn((double)mv[j].x, p.scale), offset);
+                pr[j] = make_float2((float)a, (float)b);
+            } else {
+                // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
+                const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
+                pr[j] = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
+            }
+            local += (uint32_t)d[j];
+        }
+    }
+    // warp-wide exclusive scan of the lane totals
+    uint32_t inc = local;
+#pragma unroll
+    for (int sh = 1; sh < 32; sh <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
+        if (lane >= sh) inc += v;
+    }
+    const uint32_t S = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t o = inc - local;
+
+    // the buffer must have been drained by the consumers before it is rewritten
+    mbar_wait(empty_bar, empty_parity);
+
+    float2 *par = cs.par[team][buf];
+    uint8_t *map = cs.map[team][buf];
+    uint8_t *bmap = cs.bmap[team][buf];
+    if (RAND_DWELL) {
+        const uint32_t n16 = (((S + ph + 7) >> 3) + 15) >> 4;  // boundary bytes the consumers will read, in 16-byte units
+        for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(bmap)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int m = m0 + j;
+            if (m < nk_tile) {
+                par[m] = pr[j];
+                if (RAND_DWELL) {
+                    // chunks whose first (clipped) sample falls inside this k-mer
+                    uint32_t w0 = m == 0 ? 0u : (o + ph + 7) >> 3;
+                    const uint32_t w1 = (o + (uint32_t)d[j] + ph + 7) >> 3;
+                    if (w0 < w1) map[w0] = (uint8_t)m;
+                    if (w0 + 1 < w1) map[w0 + 1] = (uint8_t)m;
+                    for (w0 += 2; w0 < w1; w0++) map[w0] = (uint8_t)m;
+                    const uint32_t pos = o + ph;  // this k-mer starts at bit (pos&7) of chunk (pos>>3)
+                    atomicOr(reinterpret_cast<uint32_t *>(bmap) + (pos >> 5), 1u << (pos & 31));
+                }
+                if (p.want_ss) p.ss[p.reads[seg.read].ss_off + seg.k0 + kstart + m] = d[j];
+                o += (uint32_t)d[j];
+            }
+        }
+    }
+    if (lane == 0) {
+        TileHdr h;
+        h.S = RAND_DWELL ? S : (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
+        h.ph = ph; h.B = B; h.L = L; h.r_lo = key.r_lo; h.r_hi = key.r_hi;
+        h.out_lo = (uint32_t)(uint64_t)out; h.out_hi = (uint32_t)((uint64_t)out >> 32);
+        cs.hdr[team][buf] = h;
+    }
+    __syncwarp();
+}
+
+// dynamic shared memory: [K4Shared][Z16: 128 KB if USE_Z][model: num_kmer*8 B if MODEL_SMEM]
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
 __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
     constexpr bool USE_Z = NOISY || RAND_DWELL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    CtaShared &cs = *reinterpret_cast<CtaShared *>(smem_raw);
-    __half *z16s = reinterpret_cast<__half *>(smem_raw + ((sizeof(CtaShared) + 127) & ~127u));
+    K4Shared &cs = *reinterpret_cast<K4Shared *>(smem_raw);
+    __half *z16s = reinterpret_cast<__half *>(smem_raw + ((sizeof(K4Shared) + 127) & ~127u));
     float2 *models = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(z16s) + (USE_Z ? Z16_N * 2 : 0));
     const int tid = threadIdx.x;
-    const int group = tid / GT;
-    const int gtid = tid - group * GT;
-    const int lane = tid & 31, gwarp = gtid >> 5;
-    TileState &ts = cs.ts[group];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int team = warp / TEAM_WARPS, role = warp % TEAM_WARPS;  // role 0 = producer
 
-    // ---- one-time staging: quantile table and (small) pore model by TMA bulk copies ----
-    if (tid == 0) mbar_init(&cs.mbar, 1);
+    // ---- prologue: tables and barriers ----
+    if (tid == 0) {
+        mbar_init(&cs.stage_bar, 1);
+        for (int t = 0; t < NTEAM; t++)
+            for (int b = 0; b < NBUF; b++) {
+                mbar_init(&cs.full[t][b], 1);
+                mbar_init(&cs.empty[t][b], NCONS);
+            }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     for (int i = tid; i < 256; i += K4_THREADS) {
         cs.code[i] = base_code(i);
         uint32_t f[8], cnt = 0;
@@ -393,207 +617,44 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
     if (tid == 0) {
         uint32_t bytes = 0;
         if (USE_Z) bytes += Z16_N * 2;
-        if (p.model_in_smem) bytes += p.num_kmer * 8;
+        if (MODEL_SMEM) bytes += p.num_kmer * 8;
         if (bytes) {
-            mbar_expect_tx(&cs.mbar, bytes);
+            mbar_expect_tx(&cs.stage_bar, bytes);
             if (USE_Z) {
-                tma_load_1d(z16s, p.z16, Z16_N, &cs.mbar);  // two 64 KB bulk copies
-                tma_load_1d(z16s + Z16_N / 2, p.z16 + Z16_N / 2, Z16_N, &cs.mbar);
+                tma_load_1d(z16s, p.z16, Z16_N, &cs.stage_bar);  // two 64 KB bulk copies
+                tma_load_1d(z16s + Z16_N / 2, p.z16 + Z16_N / 2, Z16_N, &cs.stage_bar);
             }
-            if (p.model_in_smem) tma_load_1d(models, p.model, p.num_kmer * 8, &cs.mbar);
+            if (MODEL_SMEM) tma_load_1d(models, p.model, p.num_kmer * 8, &cs.stage_bar);
         }
     }
-    if (USE_Z || p.model_in_smem) mbar_wait(&cs.mbar, 0);
-    const float2 *__restrict__ model = p.model_in_smem ? models : p.model;
-    const uint32_t zbase = smem_u32(z16s);
-    const uint32_t par_addr = smem_u32(ts.par);  // < 64 KB: the tile states lead the shared-memory layout
-    if (par_addr + (MAX_T + 8) * 8 >= 0x10000u) __trap();
+    if (USE_Z || MODEL_SMEM) mbar_wait(&cs.stage_bar, 0);
+    if (smem_u32(&cs.par[NTEAM - 1][NBUF - 1][TK - 1]) + 64 >= 0x10000u) __trap();
 
-    for (int tile = blockIdx.x * GROUPS + group; tile < p.n_tiles; tile += gridDim.x * GROUPS) {
-        const int si = p.tile_seg[tile];
-        const SegDesc seg = p.segs[si];
-        const int kstart = (tile - seg.tile0) * p.T;
-        const int nk_tile = min(p.T, seg.nk - kstart);
-        TileCtx c;
-        c.key = make_key(p, seg.read);
-        c.B = p.tile_base[tile];  // first logical sample of the tile within the read
-        c.L = p.read_siglen[seg.read];
-        c.out = p.sig + p.read_sigoff[seg.read];
-        // chunk w covers tile samples [8w-ph, 8w-ph+8): chunks are aligned in the EMITTED signal
-        c.ph = REV ? ((c.B - c.L) & 7u) : (c.B & 7u);
-        const double offset = p.read_offset[seg.read];
-
-        // ---- phase A0: digits of the tile's base window; clear the boundary bitmap ----
-        const int nb = nk_tile + p.k - 1;
-        for (int i = gtid; i < nb; i += GT) {
-            const int pos = kstart + i;
-            const uint8_t ch = pos < seg.len_a ? p.bases[seg.off_a + pos] : p.bases[seg.off_b + (pos - seg.len_a)];
-            const uint8_t code = cs.code[ch];
-            ts.digit[i] = METH ? (code >> 4) : (code & 3);
+    // ---- main loop: team-private tile sequence, NBUF-deep ring ----
+    const int gteam = blockIdx.x * NTEAM + team;
+    const int tstride = gridDim.x * NTEAM;
+    if (role == 0) {
+        const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
+        int it = 0;
+        for (int tile = gteam; tile < p.n_tiles; tile += tstride, it++) {
+            const int buf = it % NBUF;
+            const uint32_t parity = (uint32_t)((it / NBUF) & 1);
+            produce_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, cs, team, buf, tile, lane, model, z16s,
+                                                                  &cs.empty[team][buf], parity ^ 1u);
+            if (lane == 0) mbar_arrive(&cs.full[team][buf]);
         }
-        if (RAND_DWELL)
-            for (int i = gtid; i < MAP_CAP / 16; i += GT) reinterpret_cast<uint4 *>(ts.bmap)[i] = make_uint4(0, 0, 0, 0);
-        group_sync(group);
-
-        // ---- phase A1: 4 k-mers per thread: rank, model lookup, dwell, parameters ----
-        const int m0 = gtid * 4;  // first k-mer of this thread within the tile (T/4 <= 256 <= GT)
-        const bool active = m0 < nk_tile;
-        int d[4] = {0, 0, 0, 0};
-        uint32_t local = 0;
-        float2 pr[4];
-        if (active) {
-            if (RAND_DWELL) {
-                const uint32_t kidx = (uint32_t)(seg.k0_rng + kstart + m0);  // draw index of the first k-mer (multiple of 4)
-                const uint4 w = philox4x32_10(kidx >> 3, c.key.r_lo, c.key.r_hi, ST_DWELL, c.key.k0, c.key.k1);
-                const uint32_t wa = (kidx & 4) ? w.z : w.x, wb = (kidx & 4) ? w.w : w.y;
-                const uint32_t hh[4] = {wa & 0xFFFFu, wa >> 16, wb & 0xFFFFu, wb >> 16};
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    d[j] = dwell_from_z(z16(z16s, p.z2, hh[j], kidx + j, c.key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) d[j] = p.sps_fixed;
-            }
-            uint32_t rank = 0;
-            const uint8_t *dg = ts.digit + m0;
-            for (int i = 0; i < p.k - 1; i++) rank = METH ? rank * 5 + dg[i] : (rank << 2) | dg[i];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool valid = m0 + j < nk_tile;
-                if (!valid) d[j] = 0;
-                const uint32_t dn = valid ? dg[p.k - 1 + j] : 0;
-                // src/seq.h:31-42 / :62-74, rolling: drop the leading digit, append the new one
-                rank = METH ? (rank % p.kmask) * 5 + dn : ((rank << 2) | dn) & p.kmask;
-                const float2 mv = model[valid ? rank : 0];
-                if (NOISY) {
-                    const float sd = __fmul_rn(mv.y, p.amp_noise);  // float product, src/sim.c:249
-                    const double a = __dmul_rn((double)sd, p.scale);
-                    const double b = __dsub_rn(__dmul_rn((double)mv.x, p.scale), offset);
-                    pr[j] = make_float2((float)a, (float)b);
-                } else {
-                    // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
-                    const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv.x, p.digitisation), p.range), offset);
-                    pr[j] = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
-                }
-                local += (uint32_t)d[j];
-            }
+    } else {
+        const int ctid = (role - 1) * 32 + lane;
+        int it = 0;
+        for (int tile = gteam; tile < p.n_tiles; tile += tstride, it++) {
+            const int buf = it % NBUF;
+            const uint32_t parity = (uint32_t)((it / NBUF) & 1);
+            mbar_wait(&cs.full[team][buf], parity);
+            const TileHdr h = cs.hdr[team][buf];
+            consume_tile<NOISY, RAND_DWELL, REV>(p, cs.par[team][buf], cs.map[team][buf], cs.bmap[team][buf], cs.lut, z16s, h, ctid);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.empty[team][buf]);
         }
-        uint32_t o = 0, S;
-        if (RAND_DWELL) {
-            // group-wide exclusive scan of `local`
-            uint32_t inc = local;
-#pragma unroll
-            for (int sh = 1; sh < 32; sh <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
-                if (lane >= sh) inc += v;
-            }
-            if (lane == 31) ts.warp_sum[gwarp] = inc;
-            group_sync(group);
-            if (gwarp == 0) {
-                const uint32_t ws = lane < GT / 32 ? ts.warp_sum[lane] : 0;
-                uint32_t winc = ws;
-#pragma unroll
-                for (int sh = 1; sh < 16; sh <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, winc, sh);
-                    if (lane >= sh) winc += v;
-                }
-                if (lane < GT / 32) ts.warp_sum[lane] = winc - ws;
-                if (lane == GT / 32 - 1) ts.S = winc;
-            }
-            group_sync(group);
-            S = ts.S;
-            o = ts.warp_sum[gwarp] + inc - local;
-        } else {
-            S = (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
-            o = (uint32_t)m0 * (uint32_t)p.sps_fixed;
-        }
-        c.S = S;
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int m = m0 + j;
-                if (m < nk_tile) {
-                    ts.par[m] = pr[j];
-                    if (RAND_DWELL) {
-                        ts.off[m] = o;
-                        // chunks whose first (clipped) sample falls inside this k-mer
-                        uint32_t w0 = m == 0 ? 0u : (o + c.ph + 7) >> 3;
-                        const uint32_t w1 = (o + (uint32_t)d[j] + c.ph + 7) >> 3;
-                        for (; w0 < w1; w0++) ts.map[w0] = (uint16_t)m;
-                        const uint32_t pos = o + c.ph;  // boundary bit: this k-mer starts at bit (pos&7) of chunk (pos>>3)
-                        atomicOr(&ts.bmap[pos >> 5], 1u << (pos & 31));
-                    }
-                    if (p.want_ss) p.ss[p.reads[seg.read].ss_off + seg.k0 + kstart + m] = d[j];
-                    o += (uint32_t)d[j];
-                }
-            }
-            if (RAND_DWELL && m0 + 4 >= nk_tile) ts.off[nk_tile] = S;
-        }
-        group_sync(group);
-
-        // ---- phase B: samples.  One thread = one 16-byte chunk of the emitted signal. ----
-        const uint32_t nW = (S + c.ph + 7) >> 3;
-        for (uint32_t w = gtid; w < nW; w += GT) {
-            const int s0 = (int)(8 * w) - (int)c.ph;  // first tile sample of the chunk (may be < 0)
-            if (s0 < 0 || (uint32_t)(s0 + 8) > S) {
-                slow_chunk<NOISY, RAND_DWELL, REV>(p, ts, z16s, c, w);
-                continue;
-            }
-            const uint32_t q0 = REV ? (c.L - c.B - (uint32_t)(s0 + 8)) : (c.B + (uint32_t)s0);  // emitted position, multiple of 8
-            // k-mer of the first sample and the boundary mask of the chunk
-            uint32_t k0, bm;
-            if (RAND_DWELL) {
-                k0 = ts.map[w];
-                bm = reinterpret_cast<const uint8_t *>(ts.bmap)[w] & 0xFEu;
-            } else {
-                k0 = div_sps(p, (uint32_t)s0);
-                bm = 0;
-                for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - (uint32_t)s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << b;
-            }
-            const uint4 lu = cs.lut[bm];
-            const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
-            const uint32_t pa[4] = {lu.x + rep, lu.y + rep, lu.z + rep, lu.w + rep};
-            uint32_t v[8];
-            if (NOISY) {
-                const uint4 r4 = philox4x32_10(q0 >> 3, c.key.r_lo, c.key.r_hi, ST_AMP, c.key.k0, c.key.k1);
-                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-                float zmax = 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
-                    const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
-                    const uint32_t h = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
-                    const float z = lds_half(zbase + 2u * h);  // extract + one multiply-add for the address
-                    zmax = fmaxf(zmax, fabsf(z));
-                    v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
-                }
-                if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
-                    // rare: some draw fell into one of the 16 outermost cells -> refine it (10 more bits)
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int e = REV ? 7 - j : j;
-                        const uint32_t h = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
-                        if ((h & 0x7FFFu) >= Z_TAIL_FIRST) {
-                            const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
-                            const float z = z16_tail(p.z2, h, q0 + e, c.key, ST_AMP_TAIL);
-                            v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int e = REV ? 7 - j : j;
-                    const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
-                    v[e] = __float_as_uint(ab.y);
-                }
-            }
-            // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
-            const uint4 pk = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
-                                        __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
-            __stcs(reinterpret_cast<uint4 *>(c.out + q0), pk);
-        }
-        group_sync(group);  // the tile state is reused by this group's next tile
     }
 }
 
