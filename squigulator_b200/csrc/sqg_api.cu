@@ -99,8 +99,8 @@ struct Slot {
     DevBuf<uint8_t> d_bases;
     DevBuf<SegDesc> d_segs;
     DevBuf<ReadDesc> d_reads;
-    DevBuf<int32_t> d_tile_seg;
-    DevBuf<uint32_t> d_tile_sum, d_tile_base, d_siglen, d_n0;
+    DevBuf<TileDesc> d_tiles;
+    DevBuf<uint32_t> d_tile_sum, d_siglen, d_n0;
     DevBuf<int64_t> d_sigoff, d_meta;
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
@@ -118,8 +118,8 @@ struct Slot {
     int64_t arena_need = 0, total_samples = 0;
     bool const_written = false;
     void release() {
-        d_bases.release(); d_segs.release(); d_reads.release(); d_tile_seg.release(); d_tile_sum.release();
-        d_tile_base.release(); d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
+        d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release();
+        d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
         d_offset.release(); d_median.release(); d_sig.release(); d_ss.release();
         h_segs.release(); h_reads.release(); h_meta.release(); h_sigoff.release(); h_len64.release();
         h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
@@ -328,9 +328,8 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     if (nseg) CU(cudaMemcpyAsync(s.d_segs.p, s.h_segs.p, (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s.stream));
     if (n_reads) CU(cudaMemcpyAsync(s.d_reads.p, s.h_reads.p, (size_t)n_reads * sizeof(ReadDesc), cudaMemcpyHostToDevice, s.stream));
     const size_t nt = (size_t)std::max<int64_t>(ntile, 1), nr = (size_t)std::max<int64_t>(n_reads, 1);
-    CU(s.d_tile_seg.ensure(nt, false, s.stream));
+    CU(s.d_tiles.ensure(nt, false, s.stream));
     CU(s.d_tile_sum.ensure(nt, false, s.stream));
-    CU(s.d_tile_base.ensure(nt, false, s.stream));
     CU(s.d_siglen.ensure(nr, false, s.stream));
     CU(s.d_n0.ensure(nr, false, s.stream));
     CU(s.d_sigoff.ensure(nr, false, s.stream));
@@ -345,7 +344,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
 GenParams slot_params(sqg_ctx *ctx, Slot &s) {
     GenParams p = ctx->base;
     p.bases = s.d_bases.p; p.segs = s.d_segs.p; p.reads = s.d_reads.p;
-    p.tile_seg = s.d_tile_seg.p; p.tile_sum = s.d_tile_sum.p; p.tile_base = s.d_tile_base.p;
+    p.tiles = s.d_tiles.p; p.tile_sum = s.d_tile_sum.p;
     p.read_siglen = s.d_siglen.p; p.read_n0 = s.d_n0.p; p.read_sigoff = s.d_sigoff.p;
     p.read_offset = s.d_offset.p; p.read_median = s.d_median.p; p.meta = s.d_meta.p;
     p.sig = s.d_sig.p; p.ss = s.d_ss.p;
@@ -360,7 +359,7 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
     CU(cudaMemsetAsync(s.d_meta.p, 0, 4 * sizeof(int64_t), s.stream));
-    tile_map_kernel<<<(int)((s.n_segs + 255) / 256), 256, 0, s.stream>>>(p);
+    tile_desc_kernel<<<(int)((s.n_segs + 255) / 256), 256, 0, s.stream>>>(p);
     ctx->launches++;
     if (ctx->rand_dwell) {
         const int tiles_per_cta = K1_THREADS / 32;

@@ -36,6 +36,20 @@ struct ReadDesc {
     int32_t pad;
 };
 
+// Everything the dwell pass and the signal kernel need to know about a tile, in one 48-byte record
+// (written by K0, completed by K2) so that a producer warp reaches its bases with a single dependent load.
+struct __align__(16) TileDesc {
+    int64_t a_off;   // window byte i < a_rem is bases[a_off + i]   (piece a of the segment)
+    int64_t b_off;   // window byte i >= a_rem is bases[b_off + i]  (piece b)
+    int32_t a_rem;   // may be <= 0 or beyond the window
+    int32_t nk;      // k-mers in the tile
+    int32_t read;    // local read index
+    uint32_t kidx0;  // dwell draw index of the tile's first k-mer (multiple of 8)
+    int64_t ss_pos;  // where the tile's dwells go in ss[]
+    uint32_t B;      // first logical sample of the tile within the read (filled by K2)
+    uint32_t pad;
+};
+
 struct GenParams {
     // inputs
     const uint8_t *bases;
@@ -44,10 +58,9 @@ struct GenParams {
     const float2 *model;  // (level_mean, level_stdv) by rank
     const __half *z16;    // Z16[65536]
     const float *z2;      // Z2[16*1024]
-    // plan (written by K1-K3, read by K4)
-    int32_t *tile_seg;
+    // plan (written by K0-K3, read by K4)
+    TileDesc *tiles;
     uint32_t *tile_sum;
-    uint32_t *tile_base;
     uint32_t *read_siglen;
     uint32_t *read_n0;
     int64_t *read_sigoff;
@@ -109,12 +122,27 @@ __device__ __forceinline__ int find_seg(const SegDesc *__restrict__ segs, int n_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: tile -> segment map (one thread per segment)
-__global__ void __launch_bounds__(256) tile_map_kernel(const __grid_constant__ GenParams p) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n_segs) return;
-    const int t0 = p.segs[s].tile0, nt = (p.segs[s].nk + p.T - 1) / p.T;
-    for (int t = 0; t < nt; t++) p.tile_seg[t0 + t] = s;
+// K0: tile descriptors (one thread per segment)
+__global__ void __launch_bounds__(256) tile_desc_kernel(const __grid_constant__ GenParams p) {
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= p.n_segs) return;
+    const SegDesc seg = p.segs[si];
+    const int64_t ss0 = p.reads[seg.read].ss_off + seg.k0;
+    const int nt = (seg.nk + p.T - 1) / p.T;
+    for (int t = 0; t < nt; t++) {
+        const int kstart = t * p.T;
+        TileDesc d;
+        d.a_off = seg.off_a + kstart;
+        d.b_off = seg.off_b + kstart - seg.len_a;
+        d.a_rem = seg.len_a - kstart;
+        d.nk = min(p.T, seg.nk - kstart);
+        d.read = seg.read;
+        d.kidx0 = (uint32_t)(seg.k0_rng + kstart);
+        d.ss_pos = ss0 + kstart;
+        d.B = 0;
+        d.pad = 0;
+        p.tiles[seg.tile0 + t] = d;
+    }
 }
 
 // K1: per-tile sum of dwells (random-dwell modes only).  One warp per tile, one lane per Philox block of 8 k-mers.
@@ -122,13 +150,11 @@ __global__ void __launch_bounds__(K1_THREADS) dwell_sum_kernel(const __grid_cons
     const int tile = blockIdx.x * (K1_THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tile >= p.n_tiles) return;
-    const SegDesc seg = p.segs[p.tile_seg[tile]];
-    const int kstart = (tile - seg.tile0) * p.T;
-    const int nk_tile = min(p.T, seg.nk - kstart);
-    const RngKey key = make_key(p, seg.read);
+    const int nk_tile = p.tiles[tile].nk;
+    const RngKey key = make_key(p, p.tiles[tile].read);
     uint32_t sum = 0;
     if (lane * 8 < nk_tile) {
-        const uint32_t blk = (uint32_t)((seg.k0_rng + kstart) >> 3) + lane;
+        const uint32_t blk = (p.tiles[tile].kidx0 >> 3) + lane;
         const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -163,7 +189,7 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
                 sum = (uint32_t)min(p.T, seg.nk - t * p.T) * (uint32_t)p.sps_fixed;
                 p.tile_sum[tile] = sum;
             }
-            p.tile_base[tile] = (uint32_t)total;
+            p.tiles[tile].B = (uint32_t)total;
             total += sum;
         }
         if (s == rd.seg0) n0 = (uint32_t)total;
@@ -243,20 +269,21 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // K4: the signal kernel.
 //
-// A CTA is NTEAM independent TEAMS of (1 producer warp + NCONS consumer warps) that share only the read-only
+// A CTA is NTEAM independent TEAMS of (2 producer warps + NCONS consumer warps) that share only the read-only
 // tables in shared memory (quantile table, boundary LUT, base codes, small pore models).  A team works through
 // its own sequence of tiles with a ring of NBUF tile buffers handed over by mbarriers — there is no CTA-wide
 // barrier after the prologue, so k-mer preparation (latency-bound: model gathers, scan) always overlaps sample
 // emission (issue-bound).
-//   producer lane  : 8 consecutive k-mers = one Philox dwell block: digits -> ranks -> (mean,stdv) -> (A',B'),
-//                    8 dwells, warp scan, then the tile buffer: par[], chunk->k-mer map, boundary bitmap
+//   producer lane  : 8 consecutive k-mers.  "dwell" warp: one Philox dwell block -> 8 dwells, warp scan, chunk->k-mer
+//                    map + boundary bitmap.  "level" warp: digits -> ranks -> (mean,stdv) gathers -> (A',B') into par[]
 //   consumer thread: one 16-byte chunk (8 samples) of the emitted signal per iteration: k-mer of the first
 //                    sample from the map, the chunk's boundary byte -> LUT -> the 8 parameter addresses,
 //                    one Philox block -> 8 table normals -> FFMA -> cvt.rzi -> 128-bit store
 
-constexpr int NTEAM = 6;     // teams per CTA
-constexpr int NCONS = 3;     // consumer warps per team
-constexpr int TEAM_WARPS = 1 + NCONS;
+constexpr int NTEAM = 4;     // teams per CTA
+constexpr int NPROD = 2;     // producer warps per team: warp 0 = dwells/scan/map, warp 1 = bases/ranks/levels
+constexpr int NCONS = 4;     // consumer warps per team
+constexpr int TEAM_WARPS = NPROD + NCONS;
 constexpr int K4_THREADS = NTEAM * TEAM_WARPS * 32;  // 768
 constexpr int NBUF = 2;      // tile buffers per team
 constexpr int TK = 256;      // k-mers per tile (32 lanes x 8)
@@ -278,7 +305,8 @@ struct __align__(16) K4Shared {
     uint8_t bmap[NTEAM][NBUF][MAPC];  // byte w: bit b set <=> a k-mer starts at sample b of chunk w (random dwell)
     TileHdr hdr[NTEAM][NBUF];
     uint8_t digit[NTEAM][DIG_BYTES];  // producer-private: base digits of the tile's window
-    uint4 lut[256];                   // boundary byte -> 8 x 16-bit byte offsets (8 * k-mers passed)
+    uint4 lut[128 * 8];               // boundary byte>>1 -> 8 x 16-bit byte offsets (8 * k-mers passed); 8 interleaved
+                                      // copies (one per 16-byte bank group) keep a quarter-warp's LDS.128 conflict-free
     uint8_t code[256];                // base -> digits
     unsigned long long full[NTEAM][NBUF], empty[NTEAM][NBUF], stage_bar;
 };
@@ -316,12 +344,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t par
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE_%=;\n"
         "bra WAIT_LOOP_%=;\n"
         "WAIT_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(mbar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning through issue slots
         : "memory");
 }
 
@@ -387,13 +415,13 @@ __device__ __forceinline__ void consume_tile(const GenParams &p, const float2 *p
         uint32_t k0, bm;
         if (RAND_DWELL) {
             k0 = map[w];
-            bm = bmap[w] & 0xFEu;
+            bm = bmap[w] >> 1;
         } else {
             k0 = div_sps(p, (uint32_t)s0);
             bm = 0;
-            for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - (uint32_t)s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << b;
+            for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - (uint32_t)s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << (b - 1);
         }
-        const uint4 lu = lut[bm];
+        const uint4 lu = lut[bm * 8 + (ctid & 7)];
         const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
         const uint32_t pa[4] = {lu.x + rep, lu.y + rep, lu.z + rep, lu.w + rep};
         uint32_t v[8];
@@ -441,142 +469,205 @@ __device__ __forceinline__ void consume_tile(const GenParams &p, const float2 *p
 
 // ---- producer side -----------------------------------------------------------------------------------------
 
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
-__device__ __forceinline__ void produce_tile(const GenParams &p, K4Shared &cs, int team, int buf, int tile, int lane,
-                                             const float2 *__restrict__ model, const __half *z16s,
-                                             unsigned long long *empty_bar, uint32_t empty_parity) {
-    const int si = p.tile_seg[tile];
-    const SegDesc seg = p.segs[si];
-    const int kstart = (tile - seg.tile0) * p.T;
-    const int nk_tile = min(p.T, seg.nk - kstart);
-    const RngKey key = make_key(p, seg.read);
-    const uint32_t B = p.tile_base[tile];
-    const uint32_t L = p.read_siglen[seg.read];
-    const double offset = p.read_offset[seg.read];
-    int16_t *out = p.sig + p.read_sigoff[seg.read];
+__device__ __forceinline__ TileDesc load_tile_desc(const TileDesc *__restrict__ tiles, int tile) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(tiles + tile);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    TileDesc d;
+    d.a_off = (int64_t)(((uint64_t)a.y << 32) | a.x);
+    d.b_off = (int64_t)(((uint64_t)a.w << 32) | a.z);
+    d.a_rem = (int32_t)b.x; d.nk = (int32_t)b.y; d.read = (int32_t)b.z; d.kidx0 = b.w;
+    d.ss_pos = (int64_t)(((uint64_t)c.y << 32) | c.x);
+    d.B = c.z; d.pad = 0;
+    return d;
+}
+
+constexpr int WIN_LOADS = (TK + 8 + 31) / 32;  // byte loads per lane for a tile's base window (k <= 9)
+
+// Producer warp 0: dwells (src/gensig.c:255-256), their scan, the chunk->k-mer map, the boundary bitmap, the header.
+template <bool RAND_DWELL, bool REV>
+__device__ __forceinline__ void produce_dwells(const GenParams &p, K4Shared &cs, int team, int buf, const TileDesc td, int lane,
+                                               const __half *z16s, unsigned long long *empty_bar, uint32_t empty_parity) {
+    const int nk_tile = td.nk;
+    const uint32_t L = __ldg(p.read_siglen + td.read);
+    const int64_t sigoff = __ldg(p.read_sigoff + td.read);
+    const RngKey key = make_key(p, td.read);
+    const uint32_t B = td.B;
     const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
-
-    // digits of the tile's base window (coalesced byte loads; the code table folds IUPAC letters, src/seq.h:14-28)
-    uint8_t *dig = cs.digit[team];
-    const int nb = nk_tile + p.k - 1;
-    for (int i = lane; i < nb; i += 32) {
-        const int pos = kstart + i;
-        const uint8_t ch = pos < seg.len_a ? p.bases[seg.off_a + pos] : p.bases[seg.off_b + (pos - seg.len_a)];
-        const uint8_t code = cs.code[ch];
-        dig[i] = METH ? (code >> 4) : (code & 3);
-    }
-    __syncwarp();
-
-    // this lane's 8 k-mers
     const int m0 = lane * 8;
     const bool active = m0 < nk_tile;
     int d[8];
-    float2 pr[8];
-    uint32_t local = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) d[j] = 0;
-    if (active) {
-        if (RAND_DWELL) {
-            const uint32_t blk = (uint32_t)((seg.k0_rng + kstart + m0) >> 3);
-            const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                d[j] = dwell_from_z(z16(z16s, p.z2, halfword(w, j), blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) d[j] = p.sps_fixed;
-        }
-        // 16 digits: k-1 to prime the rank, then one per k-mer (k <= 9)
-        const uint2 dwa = *reinterpret_cast<const uint2 *>(dig + m0);
-        const uint2 dwb = *reinterpret_cast<const uint2 *>(dig + m0 + 8);
-        const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
-        uint32_t rank = 0;
-        const int km1 = p.k - 1;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (i < km1) {
-                const uint32_t dg = (dw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                rank = METH ? rank * 5 + dg : (rank << 2) | dg;
-            }
-        }
-        uint32_t ranks[8];
+    uint32_t o = 0, S = (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
+    if (RAND_DWELL) {
+        // this lane's 8 k-mers = one Philox block
+        const uint32_t blk = (td.kidx0 >> 3) + lane;
+        const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
+        const uint32_t zbase = smem_u32(z16s);
+        float zmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            // digit km1 + j: a dynamic byte index into the 16 staged digits
-            const int bi = km1 + j;
-            const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
-            const uint32_t dn = (word >> (8 * (bi & 3))) & 0xFFu;
-            // src/seq.h:31-42 / :62-74, rolling: drop the leading digit, append the new one
-            rank = METH ? (rank % p.kmask) * 5 + dn : ((rank << 2) | dn) & p.kmask;
-            ranks[j] = (m0 + j < nk_tile) ? rank : 0;
+            const float z = lds_half(zbase + 2u * halfword(w, j));
+            zmax = fmaxf(zmax, fabsf(z));
+            d[j] = dwell_from_z(z, p.dwell_mean, p.dwell_std);
         }
-        float2 mv[8];
+        if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) mv[j] = MODEL_SMEM ? model[ranks[j]] : __ldg(&model[ranks[j]]);
+            for (int j = 0; j < 8; j++) {
+                const uint32_t hw = halfword(w, j);
+                if ((hw & 0x7FFFu) >= Z_TAIL_FIRST)
+                    d[j] = dwell_from_z(z16_tail(p.z2, hw, blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
+            }
+        }
+        uint32_t local = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (m0 + j >= nk_tile) d[j] = 0;
-            if (NOISY) {
-                const float sd = __fmul_rn(mv[j].y, p.amp_noise);  // float product, src/sim.c:249
-                const double a = __dmul_rn((double)sd, p.scale);
-                const double b = __dsub_rn(__dmul_rn((double)mv[j].x, p.scale), offset);
-                pr[j] = make_float2((float)a, (float)b);
-            } else {
-                // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
-                const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
-                pr[j] = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
-            }
             local += (uint32_t)d[j];
         }
-    }
-    // warp-wide exclusive scan of the lane totals
-    uint32_t inc = local;
+        uint32_t inc = local;  // warp-wide scan of the lane totals
 #pragma unroll
-    for (int sh = 1; sh < 32; sh <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
-        if (lane >= sh) inc += v;
+        for (int sh = 1; sh < 32; sh <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
+            if (lane >= sh) inc += v;
+        }
+        S = __shfl_sync(0xffffffffu, inc, 31);
+        o = inc - local;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j] = (m0 + j < nk_tile) ? p.sps_fixed : 0;
     }
-    const uint32_t S = __shfl_sync(0xffffffffu, inc, 31);
-    uint32_t o = inc - local;
 
     // the buffer must have been drained by the consumers before it is rewritten
     mbar_wait(empty_bar, empty_parity);
-
-    float2 *par = cs.par[team][buf];
-    uint8_t *map = cs.map[team][buf];
-    uint8_t *bmap = cs.bmap[team][buf];
     if (RAND_DWELL) {
+        uint8_t *map = cs.map[team][buf];
+        uint8_t *bmap = cs.bmap[team][buf];
         const uint32_t n16 = (((S + ph + 7) >> 3) + 15) >> 4;  // boundary bytes the consumers will read, in 16-byte units
         for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(bmap)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-    }
-    if (active) {
+        if (active) {
+            uint32_t oo = o;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int m = m0 + j;
-            if (m < nk_tile) {
-                par[m] = pr[j];
-                if (RAND_DWELL) {
-                    // chunks whose first (clipped) sample falls inside this k-mer
-                    uint32_t w0 = m == 0 ? 0u : (o + ph + 7) >> 3;
-                    const uint32_t w1 = (o + (uint32_t)d[j] + ph + 7) >> 3;
+            for (int j = 0; j < 8; j++) {
+                const int m = m0 + j;
+                if (m < nk_tile) {
+                    // chunks whose first (clipped) sample falls inside this k-mer get it as their first k-mer
+                    const uint32_t pos = oo + ph;  // the k-mer starts at bit (pos&7) of chunk (pos>>3)
+                    uint32_t w0 = m == 0 ? 0u : (pos + 7) >> 3;
+                    const uint32_t w1 = (pos + (uint32_t)d[j] + 7) >> 3;
                     if (w0 < w1) map[w0] = (uint8_t)m;
                     if (w0 + 1 < w1) map[w0 + 1] = (uint8_t)m;
-                    for (w0 += 2; w0 < w1; w0++) map[w0] = (uint8_t)m;
-                    const uint32_t pos = o + ph;  // this k-mer starts at bit (pos&7) of chunk (pos>>3)
+                    if (w0 + 2 < w1) map[w0 + 2] = (uint8_t)m;
+                    for (w0 += 3; w0 < w1; w0++) map[w0] = (uint8_t)m;
                     atomicOr(reinterpret_cast<uint32_t *>(bmap) + (pos >> 5), 1u << (pos & 31));
+                    oo += (uint32_t)d[j];
                 }
-                if (p.want_ss) p.ss[p.reads[seg.read].ss_off + seg.k0 + kstart + m] = d[j];
-                o += (uint32_t)d[j];
             }
         }
     }
+    if (p.want_ss && active) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (m0 + j < nk_tile) p.ss[td.ss_pos + m0 + j] = d[j];
+    }
     if (lane == 0) {
+        int16_t *out = p.sig + sigoff;
         TileHdr h;
-        h.S = RAND_DWELL ? S : (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
-        h.ph = ph; h.B = B; h.L = L; h.r_lo = key.r_lo; h.r_hi = key.r_hi;
+        h.S = S; h.ph = ph; h.B = B; h.L = L; h.r_lo = key.r_lo; h.r_hi = key.r_hi;
         h.out_lo = (uint32_t)(uint64_t)out; h.out_hi = (uint32_t)((uint64_t)out >> 32);
         cs.hdr[team][buf] = h;
+    }
+    __syncwarp();
+}
+
+// Producer warp 1: bases -> digits -> ranks (src/seq.h) -> (level_mean, level_stdv) gathers -> per-k-mer (A', B').
+// Source order = latency order: the byte loads and the gathers are issued as early as their inputs allow.
+template <bool NOISY, bool METH, bool MODEL_SMEM>
+__device__ __forceinline__ void produce_levels(const GenParams &p, K4Shared &cs, int team, int buf, const TileDesc td, int lane,
+                                               const float2 *__restrict__ model, unsigned long long *empty_bar,
+                                               uint32_t empty_parity) {
+    const int nk_tile = td.nk;
+    // the tile's base window: coalesced byte loads, all in flight at once
+    uint32_t raw[WIN_LOADS];
+    const int nb = nk_tile + p.k - 1;
+#pragma unroll
+    for (int u = 0; u < WIN_LOADS; u++) {
+        const int i = lane + 32 * u;
+        raw[u] = 0;
+        if (i < nb) raw[u] = __ldg(p.bases + (i < td.a_rem ? td.a_off : td.b_off) + i);
+    }
+    const double offset = __ldg(p.read_offset + td.read);
+    const int m0 = lane * 8;
+    const bool active = m0 < nk_tile;
+
+    // bases -> digits (the code table folds IUPAC letters, src/seq.h:14-28 / :45-60)
+    uint8_t *dig = cs.digit[team];
+#pragma unroll
+    for (int u = 0; u < WIN_LOADS; u++) {
+        const int i = lane + 32 * u;
+        const uint32_t code = cs.code[raw[u] & 0xFFu];
+        if (i < nb) dig[i] = (uint8_t)(METH ? (code >> 4) : (code & 3u));
+    }
+    __syncwarp();
+
+    // ranks of this lane's 8 k-mers (src/seq.h:31-42 / :62-74)
+    uint32_t ranks[8];
+    {
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(dig + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(dig + m0 + 8);
+        if (!METH) {
+            // 16 two-bit digits packed first-digit-most-significant: ((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes
+            const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
+                               ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
+            const int sh0 = 32 - 2 * p.k;
+#pragma unroll
+            for (int j = 0; j < 8; j++) ranks[j] = (P >> (sh0 - 2 * j)) & p.kmask;
+        } else {
+            const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
+            const int km1 = p.k - 1;
+            uint32_t rank = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < km1) rank = rank * 5 + ((dw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int bi = km1 + j;
+                const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
+                rank = (rank % p.kmask) * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);
+                ranks[j] = rank;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (m0 + j >= nk_tile) ranks[j] = 0;
+    }
+    __syncwarp();  // every lane has read its digits: the staging area may be rewritten for the next tile
+    float2 mv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) mv[j] = MODEL_SMEM ? model[ranks[j]] : __ldg(&model[ranks[j]]);
+
+    // per-k-mer parameters
+    float2 pr[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (NOISY) {
+            const float sd = __fmul_rn(mv[j].y, p.amp_noise);  // float product, src/sim.c:249
+            const double a = __dmul_rn((double)sd, p.scale);
+            const double b = __dsub_rn(__dmul_rn((double)mv[j].x, p.scale), offset);
+            pr[j] = make_float2((float)a, (float)b);
+        } else {
+            // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
+            const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
+            pr[j] = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
+        }
+    }
+    mbar_wait(empty_bar, empty_parity);
+    if (active) {
+        float2 *par = cs.par[team][buf] + m0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            // 16-byte stores: two k-mers at a time (rows beyond the tile are never read)
+            *reinterpret_cast<float4 *>(par + j) = make_float4(pr[j].x, pr[j].y, pr[j + 1].x, pr[j + 1].y);
+        }
     }
     __syncwarp();
 }
@@ -598,17 +689,18 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
         mbar_init(&cs.stage_bar, 1);
         for (int t = 0; t < NTEAM; t++)
             for (int b = 0; b < NBUF; b++) {
-                mbar_init(&cs.full[t][b], 1);
+                mbar_init(&cs.full[t][b], NPROD);
                 mbar_init(&cs.empty[t][b], NCONS);
             }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int i = tid; i < 256; i += K4_THREADS) {
-        cs.code[i] = base_code(i);
+    for (int i = tid; i < 256; i += K4_THREADS) cs.code[i] = base_code(i);
+    for (int i = tid; i < 128 * 8; i += K4_THREADS) {
+        const int m = (i >> 3) << 1;  // boundary mask (bit 0 is never used)
         uint32_t f[8], cnt = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if (j >= 1 && ((i >> j) & 1)) cnt++;
+            if (j >= 1 && ((m >> j) & 1)) cnt++;
             f[j] = cnt * 8;
         }
         cs.lut[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
@@ -633,18 +725,23 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
     // ---- main loop: team-private tile sequence, NBUF-deep ring ----
     const int gteam = blockIdx.x * NTEAM + team;
     const int tstride = gridDim.x * NTEAM;
-    if (role == 0) {
+    if (role < NPROD) {
         const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
         int it = 0;
+        TileDesc td_next = load_tile_desc(p.tiles, min(gteam, p.n_tiles - 1));
         for (int tile = gteam; tile < p.n_tiles; tile += tstride, it++) {
             const int buf = it % NBUF;
             const uint32_t parity = (uint32_t)((it / NBUF) & 1);
-            produce_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, cs, team, buf, tile, lane, model, z16s,
-                                                                  &cs.empty[team][buf], parity ^ 1u);
+            const TileDesc td = td_next;
+            td_next = load_tile_desc(p.tiles, min(tile + tstride, p.n_tiles - 1));  // in flight during this tile
+            if (role == 0)
+                produce_dwells<RAND_DWELL, REV>(p, cs, team, buf, td, lane, z16s, &cs.empty[team][buf], parity ^ 1u);
+            else
+                produce_levels<NOISY, METH, MODEL_SMEM>(p, cs, team, buf, td, lane, model, &cs.empty[team][buf], parity ^ 1u);
             if (lane == 0) mbar_arrive(&cs.full[team][buf]);
         }
     } else {
-        const int ctid = (role - 1) * 32 + lane;
+        const int ctid = (role - NPROD) * 32 + lane;
         int it = 0;
         for (int tile = gteam; tile < p.n_tiles; tile += tstride, it++) {
             const int buf = it % NBUF;
