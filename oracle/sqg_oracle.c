@@ -141,6 +141,12 @@ float sqo_z16(const void *zt, uint32_t h, const uint32_t key[2], uint32_t c0, ui
     return half_to_float(z16[h & 0xFFFFu]);
 }
 
+/* Bank-stratified table index (DESIGN.md "z16"): bits 1-5 of the 16-bit draw are replaced by the low five
+ * bits of the draw's Philox block number.  Those bits select the shared-memory bank of the 2-byte table entry,
+ * so the 32 lanes of a warp (which handle 32 consecutive blocks) never collide; a draw still picks uniformly
+ * among 2^11 cells spread evenly over the whole table, and every table cell is used by some block residue. */
+static uint32_t stratify(uint32_t h, uint32_t block) { return (h & 0xFFC1u) | ((block & 31u) << 1); }
+
 static uint32_t halfword(const uint32_t w[4], uint32_t j) { /* j in 0..7 */
     uint32_t x = w[j >> 1];
     return (j & 1) ? (x >> 16) : (x & 0xFFFFu);
@@ -350,8 +356,8 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                 int64_t di = i < nk_seg[0] ? i : ((nk_seg[0] + 7) & ~(int64_t)7) + (i - nk_seg[0]);
                 uint32_t ctr[4] = {(uint32_t)(di >> 3), r_lo, r_hi, ST_DWELL}, w[4];
                 sqo_philox4x32_10(ctr, o->key, w);
-                float z = sqo_z16(o->zt, halfword(w, (uint32_t)(di & 7)), o->key, (uint32_t)di, r_lo, r_hi,
-                                  ST_DWELL_TAIL);
+                float z = sqo_z16(o->zt, stratify(halfword(w, (uint32_t)(di & 7)), (uint32_t)(di >> 3)), o->key,
+                                  (uint32_t)di, r_lo, r_hi, ST_DWELL_TAIL);
                 /* Philox mode: single-precision FMA, round to nearest (ties to even; the reference's
                  * round() differs only on exact .5 ties, which table normals do not produce) */
                 d = (int)lrintf(fmaf(z, (float)p->dwell_std, (float)p->dwell_mean));
@@ -391,7 +397,7 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                 uint32_t q = (uint32_t)(rna ? total - 1 - n : n);
                 uint32_t ctr[4] = {q >> 3, r_lo, r_hi, ST_AMP}, w[4];
                 sqo_philox4x32_10(ctr, o->key, w);
-                float z = sqo_z16(o->zt, halfword(w, q & 7), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
+                float z = sqo_z16(o->zt, stratify(halfword(w, q & 7), q >> 3), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
                 raw[n] = to_i16_f(fmaf(z, A, B));
             }
         }

@@ -163,6 +163,7 @@ struct sqg_ctx {
     int model_in_smem = 0;
     size_t k4_smem = 0;
     int k4_grid_per_sm = 1;
+    int k4_warps = 16;
     std::atomic<int64_t> launches{0};
     Slot sync_slot;  // used by sqg_gen_batch / sqg_gen_sig
     // dispatcher
@@ -391,11 +392,11 @@ int slot_size_arena(sqg_ctx *ctx, Slot &s) {
 int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
-    const int grid = (int)std::min<int64_t>((s.n_tiles + NTEAM - 1) / NTEAM, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
+    const int grid = (int)std::min<int64_t>((s.n_tiles + ctx->k4_warps - 1) / ctx->k4_warps, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
     if (before) CU(cudaEventRecord(before, s.stream));
     void *args[] = {(void *)&p};
-    CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(K4_THREADS), args, ctx->k4_smem, s.stream));
+    CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(ctx->k4_warps * 32), args, ctx->k4_smem, s.stream));
     if (after) CU(cudaEventRecord(after, s.stream));
     ctx->launches++;
     if (ctx->prefix && ctx->rev) {
@@ -570,18 +571,24 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     ctx->base.z16 = reinterpret_cast<const __half *>(ctx->d_z.p);
     ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z16_N * 2);
 
-    // shared-memory plan of the signal kernel: tile state + quantile table (+ the pore model when it is small:
-    // R9 6-mer = 32 KB, R9 RNA 5-mer = 8 KB)
+    // shared-memory plan of the signal kernel: per-warp tile buffers + boundary LUT + quantile table (+ the pore model
+    // when it is small: R9 6-mer = 32 KB, R9 RNA 5-mer = 8 KB).  As many warps as fit, at most K4_MAX_WARPS.
     const bool use_z = ctx->noisy || ctx->rand_dwell;
-    size_t smem = ((sizeof(K4Shared) + 127) & ~(size_t)127) + (use_z ? (size_t)Z16_N * 2 : 0);
     ctx->model_in_smem = (!ctx->meth && n <= 4096) ? 1 : 0;
-    if (ctx->model_in_smem) smem += n * sizeof(float2);
     ctx->base.model_in_smem = ctx->model_in_smem;
-    ctx->k4_smem = smem;
+    const uint32_t model_bytes = ctx->model_in_smem ? (uint32_t)(n * sizeof(float2)) : 0;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    int nw = K4_MAX_WARPS;
+    while (nw > 1 && k4_layout(nw, use_z, model_bytes).total > smem_max) nw--;
+    const K4Layout lay = k4_layout(nw, use_z, model_bytes);
+    if (lay.total > smem_max || lay.par + (uint32_t)nw * TK * 8 + 2048 >= 0x10000u)
+        return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
+    ctx->k4_warps = nw;
+    ctx->k4_smem = lay.total;
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
-    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, K4_THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, nw * 32, lay.total));
     if (occ < 1) return fail(ctx, SQG_ERR_CUDA, "signal kernel does not fit on an SM");
     ctx->k4_grid_per_sm = occ;
 

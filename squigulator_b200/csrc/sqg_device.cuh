@@ -55,6 +55,12 @@ struct RngKey {
     uint32_t r_lo, r_hi;   // global read index = counter words 1,2
 };
 
+// Bank-stratified table index: bits 1-5 of a 16-bit draw (= the shared-memory bank of its 2-byte table entry) are
+// replaced by the low five bits of the draw's Philox block number.  The 32 lanes of a warp work on 32 consecutive
+// blocks, so a warp-wide table lookup touches 32 different banks: one wavefront instead of ~3.4.  Each draw still
+// picks uniformly among 2^11 cells spread evenly over the table, and all cells are used across block residues.
+__device__ __forceinline__ uint32_t stratify(uint32_t h, uint32_t block) { return (h & 0xFFC1u) | ((block & 31u) << 1); }
+
 // rare path of z16: 10 fresh bits pick the sub-cell
 __device__ __noinline__ float z16_tail(const float *__restrict__ z2g, uint32_t h, uint32_t c0, RngKey key,
                                        uint32_t stream) {

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(K1_THREADS) dwell_sum_kernel(const __grid_cons
         const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float z = z16(p.z16, p.z2, halfword(w, j), blk * 8 + j, key, ST_DWELL_TAIL);
+            const float z = z16(p.z16, p.z2, stratify(halfword(w, j), blk), blk * 8 + j, key, ST_DWELL_TAIL);
             const int d = dwell_from_z(z, p.dwell_mean, p.dwell_std);
             if (lane * 8 + j < nk_tile) sum += (uint32_t)d;
         }
@@ -269,47 +269,52 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // K4: the signal kernel.
 //
-// A CTA is NTEAM independent TEAMS of (2 producer warps + NCONS consumer warps) that share only the read-only
-// tables in shared memory (quantile table, boundary LUT, base codes, small pore models).  A team works through
-// its own sequence of tiles with a ring of NBUF tile buffers handed over by mbarriers — there is no CTA-wide
-// barrier after the prologue, so k-mer preparation (latency-bound: model gathers, scan) always overlaps sample
-// emission (issue-bound).
-//   producer lane  : 8 consecutive k-mers.  "dwell" warp: one Philox dwell block -> 8 dwells, warp scan, chunk->k-mer
-//                    map + boundary bitmap.  "level" warp: digits -> ranks -> (mean,stdv) gathers -> (A',B') into par[]
-//   consumer thread: one 16-byte chunk (8 samples) of the emitted signal per iteration: k-mer of the first
-//                    sample from the map, the chunk's boundary byte -> LUT -> the 8 parameter addresses,
-//                    one Philox block -> 8 table normals -> FFMA -> cvt.rzi -> 128-bit store
+// Every WARP is autonomous: it owns a private tile buffer in shared memory and walks its own sequence of tiles,
+// alternating a k-mer phase (A: latency-bound — descriptor, base window, model gathers, warp scan) and a sample phase
+// (B: issue-bound — Philox, table normals, FFMA, 128-bit stores).  There are no CTA-wide barriers and no
+// producer/consumer hand-offs after the prologue; the 16-24 resident warps of an SM are at different points of their
+// tiles, so phase-A latency of some warps is covered by phase-B work of the others.  The CTA shares only read-only
+// tables: the binary16 quantile table and (when it fits) the pore model, both staged by TMA bulk copies, the boundary
+// LUT and the base-code table.
+//   phase A, lane = 8 consecutive k-mers = one Philox dwell block: 8 dwells, warp scan, chunk->k-mer map + boundary
+//            bitmap; digits -> ranks -> (mean,stdv) gathers -> (A',B') into par[]
+//   phase B, lane = one 16-byte chunk (8 samples) of the emitted signal per iteration: k-mer of the first sample from
+//            the map, the chunk's boundary byte -> LUT -> the 8 parameter addresses, one Philox block -> 8 table
+//            normals (bank-stratified lookups) -> FFMA -> cvt.rzi -> one 128-bit store
 
-constexpr int NTEAM = 4;     // teams per CTA
-constexpr int NPROD = 2;     // producer warps per team: warp 0 = dwells/scan/map, warp 1 = bases/ranks/levels
-constexpr int NCONS = 4;     // consumer warps per team
-constexpr int TEAM_WARPS = NPROD + NCONS;
-constexpr int K4_THREADS = NTEAM * TEAM_WARPS * 32;  // 768
-constexpr int NBUF = 2;      // tile buffers per team
+constexpr int K4_MAX_WARPS = 24;
+constexpr int K4_MAX_THREADS = K4_MAX_WARPS * 32;  // register budget: 65536 / 768 = 85
 constexpr int TK = 256;      // k-mers per tile (32 lanes x 8)
 constexpr int MAPC = 1280;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8
 constexpr int DIG_BYTES = TK + 32;
+constexpr int LUT_COPIES = 4;
+constexpr int NCHUNK = 1;    // 16-byte chunks per lane per phase-B iteration (more = more ILP but more code)
+constexpr int WARP_TILE_BYTES = TK * 8 + 2 * MAPC + DIG_BYTES;  // par + map + bmap + digits
 
-struct __align__(16) TileHdr {
-    uint32_t S;      // samples in the tile
-    uint32_t ph;     // chunk w covers tile samples [8w-ph, 8w-ph+8)
-    uint32_t B;      // first logical sample of the tile within the read
-    uint32_t L;      // samples in the read
-    uint32_t r_lo, r_hi;  // global read index (Philox counter words 1,2)
-    uint32_t out_lo, out_hi;  // start of the read in the signal arena
+// Shared-memory layout (dynamic), for nw warps:
+//   [par: nw*TK float2]  (first, so that parameter addresses fit 16 bits)   [map: nw*MAPC u8] [bmap: nw*MAPC u8]
+//   [digit: nw*DIG_BYTES u8] [lut: 128*LUT_COPIES uint4] [code: 256 u8] [mbar: 8 B, 16-aligned]
+//   [Z16: 128 KB, 128-aligned, if USE_Z] [model: num_kmer*8 B if MODEL_SMEM]
+struct K4Layout {
+    uint32_t par, map, bmap, digit, lut, code, mbar, z16, model, total;
 };
-
-struct __align__(16) K4Shared {
-    float2 par[NTEAM][NBUF][TK];      // must stay below 64 KB: phase B packs these addresses into 16 bits
-    uint8_t map[NTEAM][NBUF][MAPC];   // chunk -> k-mer (within the tile) of its first sample      (random dwell)
-    uint8_t bmap[NTEAM][NBUF][MAPC];  // byte w: bit b set <=> a k-mer starts at sample b of chunk w (random dwell)
-    TileHdr hdr[NTEAM][NBUF];
-    uint8_t digit[NTEAM][DIG_BYTES];  // producer-private: base digits of the tile's window
-    uint4 lut[128 * 8];               // boundary byte>>1 -> 8 x 16-bit byte offsets (8 * k-mers passed); 8 interleaved
-                                      // copies (one per 16-byte bank group) keep a quarter-warp's LDS.128 conflict-free
-    uint8_t code[256];                // base -> digits
-    unsigned long long full[NTEAM][NBUF], empty[NTEAM][NBUF], stage_bar;
-};
+__host__ __device__ inline K4Layout k4_layout(int nw, bool use_z, uint32_t model_bytes) {
+    K4Layout L;
+    uint32_t o = 0;
+    L.par = o; o += (uint32_t)nw * TK * 8;
+    L.map = o; o += (uint32_t)nw * MAPC;
+    L.bmap = o; o += (uint32_t)nw * MAPC;
+    L.digit = o; o += (uint32_t)nw * DIG_BYTES;
+    o = (o + 15u) & ~15u;
+    L.lut = o; o += 128 * LUT_COPIES * 16;
+    L.code = o; o += 256;
+    L.mbar = o; o += 16;
+    o = (o + 127u) & ~127u;
+    L.z16 = o; o += use_z ? (uint32_t)Z16_N * 2 : 0;
+    L.model = o; o += model_bytes;
+    L.total = o;
+    return L;
+}
 
 // ---- raw shared-memory access by 32-bit shared address ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -324,7 +329,7 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     return v;
 }
 
-// ---- mbarrier / TMA bulk copy (SASS: SYNCS, UBLKCP) ----
+// ---- mbarrier / TMA bulk copy for the one-time table staging (SASS: SYNCS, UBLKCP) ----
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
@@ -332,33 +337,41 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 }
 __device__ __forceinline__ void mbar_init(unsigned long long *mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra WAIT_DONE_%=;\n"
         "bra WAIT_LOOP_%=;\n"
         "WAIT_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(mbar)),
-        "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning through issue slots
+        "r"(parity)
         : "memory");
 }
 
-// ---- consumer side -----------------------------------------------------------------------------------------
+// What phase B needs to know about the tile (registers, warp-uniform)
+struct TileHdr {
+    uint32_t S;      // samples in the tile
+    uint32_t ph;     // chunk w covers tile samples [8w-ph, 8w-ph+8)
+    uint32_t B;      // first logical sample of the tile within the read
+    uint32_t L;      // samples in the read
+    uint32_t r_lo, r_hi;  // global read index (Philox counter words 1,2)
+    int16_t *out;    // start of the read in the signal arena
+};
+
+// ---- phase B ---------------------------------------------------------------------------------------------------
 
 // Generic (slow) chunk: the clipped chunks at the two ends of a tile.  Walks the boundary bits sample by sample.
 template <bool NOISY, bool RAND_DWELL, bool REV>
 __device__ __noinline__ void slow_chunk(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
-                                        const __half *__restrict__ z16s, const TileHdr h, int16_t *out, uint32_t w) {
+                                        const __half *__restrict__ z16s, const TileHdr h, uint32_t w) {
     const int s0 = (int)(8 * w) - (int)h.ph;
     const uint32_t q0 = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);
     const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
@@ -388,86 +401,127 @@ __device__ __noinline__ void slow_chunk(const GenParams &p, const float2 *par, c
         uint32_t v;
         if (NOISY) {
             const uint32_t x = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
-            const uint32_t hw = (e & 1) ? (x >> 16) : (x & 0xFFFFu);
+            const uint32_t hw = stratify((e & 1) ? (x >> 16) : (x & 0xFFFFu), q0 >> 3);
             const float z = z16(z16s, p.z2, hw, q0 + e, key, ST_AMP_TAIL);
             v = to_i16_bits(fmaf(z, ab.x, ab.y));
         } else {
             v = __float_as_uint(ab.y);
         }
-        out[q0 + e] = (int16_t)v;
+        h.out[q0 + e] = (int16_t)v;
+    }
+}
+
+// NCH chunks of the same lane (w, w+32, ...) in one straight-line block so that their Philox chains and table
+// lookups interleave (instruction-level parallelism: a warp alone sustains ~2x the issue rate).
+template <bool NOISY, bool RAND_DWELL, bool REV, int NCH>
+__device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
+                                                 const uint4 *lut, const __half *z16s, const TileHdr &h, int lane,
+                                                 const uint32_t (&wv)[NCH], const bool (&st)[NCH]) {
+    const uint32_t zbase = smem_u32(z16s);
+    const uint32_t par_addr = smem_u32(par);  // < 64 KB by layout
+    uint32_t q0[NCH], pa[NCH][4], v[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const uint32_t wc = wv[c];
+        const uint32_t s0 = 8 * wc - h.ph;  // first tile sample of the chunk
+        q0[c] = REV ? (h.L - h.B - (s0 + 8)) : (h.B + s0);  // emitted position, multiple of 8
+        uint32_t k0, bm;
+        if (RAND_DWELL) {
+            k0 = map[wc];
+            bm = bmap[wc] >> 1;
+        } else {
+            k0 = div_sps(p, s0);
+            bm = 0;
+            for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << (b - 1);
+        }
+        const uint4 lu = lut[bm * LUT_COPIES + (lane & (LUT_COPIES - 1))];
+        const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
+        pa[c][0] = lu.x + rep; pa[c][1] = lu.y + rep; pa[c][2] = lu.z + rep; pa[c][3] = lu.w + rep;
+    }
+    if (NOISY) {
+        uint32_t rw[NCH][4];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const uint4 r4 = philox4x32_10_rk(q0[c] >> 3, h.r_lo, h.r_hi, ST_AMP, p.rk);
+            rw[c][0] = r4.x; rw[c][1] = r4.y; rw[c][2] = r4.z; rw[c][3] = r4.w;
+        }
+        float zmax = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const uint32_t bank = ((q0[c] >> 3) & 31u) << 1;  // stratify(): the chunk's Philox block picks the bank
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
+                const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
+                const uint32_t hw = (((e & 1) ? (rw[c][e >> 1] >> 16) : rw[c][e >> 1]) & 0xFFC1u) | bank;
+                const float z = lds_half(zbase + 2u * hw);
+                zmax = fmaxf(zmax, fabsf(z));
+                v[c][e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
+            }
+        }
+        if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
+            // rare: some draw fell into one of the 16 outermost cells -> refine it (10 more bits)
+            const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint32_t bank = ((q0[c] >> 3) & 31u) << 1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int e = REV ? 7 - j : j;
+                    const uint32_t hw = (((e & 1) ? (rw[c][e >> 1] >> 16) : rw[c][e >> 1]) & 0xFFC1u) | bank;
+                    if ((hw & 0x7FFFu) >= Z_TAIL_FIRST) {
+                        const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
+                        const float z = z16_tail(p.z2, hw, q0[c] + e, key, ST_AMP_TAIL);
+                        v[c][e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int e = REV ? 7 - j : j;
+                const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
+                v[c][e] = __float_as_uint(ab.y);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
+        const uint4 pk = make_uint4(__byte_perm(v[c][0], v[c][1], 0x5410), __byte_perm(v[c][2], v[c][3], 0x5410),
+                                    __byte_perm(v[c][4], v[c][5], 0x5410), __byte_perm(v[c][6], v[c][7], 0x5410));
+        if (st[c]) __stcs(reinterpret_cast<uint4 *>(h.out + q0[c]), pk);
     }
 }
 
 template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __forceinline__ void consume_tile(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
-                                             const uint4 *lut, const __half *z16s, const TileHdr h, int ctid) {
-    int16_t *out = reinterpret_cast<int16_t *>(((uint64_t)h.out_hi << 32) | h.out_lo);
-    const uint32_t zbase = smem_u32(z16s);
-    const uint32_t par_addr = smem_u32(par);  // < 64 KB by layout
+__device__ __forceinline__ void emit_tile(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
+                                          const uint4 *lut, const __half *z16s, const TileHdr h, int lane) {
     const uint32_t nW = (h.S + h.ph + 7) >> 3;
-    for (uint32_t w = ctid; w < nW; w += NCONS * 32) {
-        const int s0 = (int)(8 * w) - (int)h.ph;  // first tile sample of the chunk (may be < 0)
-        if (s0 < 0 || (uint32_t)(s0 + 8) > h.S) {
-            slow_chunk<NOISY, RAND_DWELL, REV>(p, par, map, bmap, z16s, h, out, w);
-            continue;
-        }
-        const uint32_t q0 = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);  // emitted position, multiple of 8
-        uint32_t k0, bm;
-        if (RAND_DWELL) {
-            k0 = map[w];
-            bm = bmap[w] >> 1;
-        } else {
-            k0 = div_sps(p, (uint32_t)s0);
-            bm = 0;
-            for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - (uint32_t)s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << (b - 1);
-        }
-        const uint4 lu = lut[bm * 8 + (ctid & 7)];
-        const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
-        const uint32_t pa[4] = {lu.x + rep, lu.y + rep, lu.z + rep, lu.w + rep};
-        uint32_t v[8];
-        if (NOISY) {
-            const uint4 r4 = philox4x32_10_rk(q0 >> 3, h.r_lo, h.r_hi, ST_AMP, p.rk);
-            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-            float zmax = 0.f;
+    // chunks [wlo, whi) lie fully inside the tile; chunk 0 is clipped iff ph > 0, the last one iff it overhangs S
+    const uint32_t wlo = h.ph ? 1u : 0u;
+    const uint32_t whi = (h.S + h.ph) >> 3;
+    for (uint32_t w = wlo + lane; w < whi; w += 32 * NCHUNK) {
+        uint32_t wv[NCHUNK];
+        bool st[NCHUNK];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
-                const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
-                const uint32_t hw = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
-                const float z = lds_half(zbase + 2u * hw);
-                zmax = fmaxf(zmax, fabsf(z));
-                v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
-            }
-            if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
-                // rare: some draw fell into one of the 16 outermost cells -> refine it (10 more bits)
-                const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int e = REV ? 7 - j : j;
-                    const uint32_t hw = (e & 1) ? (rw[e >> 1] >> 16) : (rw[e >> 1] & 0xFFFFu);
-                    if ((hw & 0x7FFFu) >= Z_TAIL_FIRST) {
-                        const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
-                        const float z = z16_tail(p.z2, hw, q0 + e, key, ST_AMP_TAIL);
-                        v[e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
-                    }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int e = REV ? 7 - j : j;
-                const float2 ab = lds_f2((j & 1) ? (pa[j >> 1] >> 16) : (pa[j >> 1] & 0xFFFFu));
-                v[e] = __float_as_uint(ab.y);
-            }
+        for (int c = 0; c < NCHUNK; c++) {
+            st[c] = w + 32u * c < whi;
+            wv[c] = st[c] ? w + 32u * c : w;  // a missing partner is computed redundantly and not stored
         }
-        // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
-        const uint4 pk = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
-                                    __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
-        __stcs(reinterpret_cast<uint4 *>(out + q0), pk);
+        emit_chunks_fast<NOISY, RAND_DWELL, REV, NCHUNK>(p, par, map, bmap, lut, z16s, h, lane, wv, st);
+    }
+    // the (at most two) clipped chunks at the ends of the tile: generic path, both in one warp-level call
+    if (lane < 2) {
+        const uint32_t w = lane == 0 ? 0u : nW - 1;
+        const bool clipped = lane == 0 ? (wlo == 1u) : (whi < nW && !(nW == 1 && wlo == 1u));
+        if (clipped) slow_chunk<NOISY, RAND_DWELL, REV>(p, par, map, bmap, z16s, h, w);
     }
 }
 
-// ---- producer side -----------------------------------------------------------------------------------------
+// ---- phase A ---------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ TileDesc load_tile_desc(const TileDesc *__restrict__ tiles, int tile) {
     const uint4 *q = reinterpret_cast<const uint4 *>(tiles + tile);
@@ -483,36 +537,51 @@ __device__ __forceinline__ TileDesc load_tile_desc(const TileDesc *__restrict__ 
 
 constexpr int WIN_LOADS = (TK + 8 + 31) / 32;  // byte loads per lane for a tile's base window (k <= 9)
 
-// Producer warp 0: dwells (src/gensig.c:255-256), their scan, the chunk->k-mer map, the boundary bitmap, the header.
-template <bool RAND_DWELL, bool REV>
-__device__ __forceinline__ void produce_dwells(const GenParams &p, K4Shared &cs, int team, int buf, const TileDesc td, int lane,
-                                               const __half *z16s, unsigned long long *empty_bar, uint32_t empty_parity) {
+// Source order = latency order: global loads first (base window, per-read values), then the dwell draws (shared
+// memory only) while they fly, then digits -> ranks -> model gathers, then the map/bitmap scatter while the gathers fly.
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
+__device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDesc td, int lane, float2 *par, uint8_t *map,
+                                                uint8_t *bmap, uint8_t *dig, const uint8_t *code,
+                                                const float2 *__restrict__ model, const __half *z16s) {
     const int nk_tile = td.nk;
+    // (1) the tile's base window: coalesced byte loads, all in flight at once
+    uint32_t raw[WIN_LOADS];
+    const int nb = nk_tile + p.k - 1;
+    const uint8_t *pa_lane = p.bases + td.a_off + lane, *pb_lane = p.bases + td.b_off + lane;
+#pragma unroll
+    for (int u = 0; u < WIN_LOADS; u++) {
+        const int i = lane + 32 * u;
+        raw[u] = 0;
+        if (i < nb) raw[u] = __ldg((i < td.a_rem ? pa_lane : pb_lane) + 32 * u);
+    }
+    // (2) per-read values
     const uint32_t L = __ldg(p.read_siglen + td.read);
+    const double offset = __ldg(p.read_offset + td.read);
     const int64_t sigoff = __ldg(p.read_sigoff + td.read);
     const RngKey key = make_key(p, td.read);
     const uint32_t B = td.B;
     const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
     const int m0 = lane * 8;
     const bool active = m0 < nk_tile;
+
+    // (3) dwells of this lane's 8 k-mers = one Philox block (src/gensig.c:255-256), then the warp scan
     int d[8];
     uint32_t o = 0, S = (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
     if (RAND_DWELL) {
-        // this lane's 8 k-mers = one Philox block
         const uint32_t blk = (td.kidx0 >> 3) + lane;
         const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
         const uint32_t zbase = smem_u32(z16s);
         float zmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float z = lds_half(zbase + 2u * halfword(w, j));
+            const float z = lds_half(zbase + 2u * stratify(halfword(w, j), blk));
             zmax = fmaxf(zmax, fabsf(z));
             d[j] = dwell_from_z(z, p.dwell_mean, p.dwell_std);
         }
         if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t hw = halfword(w, j);
+                const uint32_t hw = stratify(halfword(w, j), blk);
                 if ((hw & 0x7FFFu) >= Z_TAIL_FIRST)
                     d[j] = dwell_from_z(z16_tail(p.z2, hw, blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
             }
@@ -523,7 +592,7 @@ __device__ __forceinline__ void produce_dwells(const GenParams &p, K4Shared &cs,
             if (m0 + j >= nk_tile) d[j] = 0;
             local += (uint32_t)d[j];
         }
-        uint32_t inc = local;  // warp-wide scan of the lane totals
+        uint32_t inc = local;
 #pragma unroll
         for (int sh = 1; sh < 32; sh <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
@@ -536,13 +605,58 @@ __device__ __forceinline__ void produce_dwells(const GenParams &p, K4Shared &cs,
         for (int j = 0; j < 8; j++) d[j] = (m0 + j < nk_tile) ? p.sps_fixed : 0;
     }
 
-    // the buffer must have been drained by the consumers before it is rewritten
-    mbar_wait(empty_bar, empty_parity);
+    // (4) bases -> digits (the code table folds IUPAC letters, src/seq.h:14-28 / :45-60)
+#pragma unroll
+    for (int u = 0; u < WIN_LOADS; u++) {
+        const int i = lane + 32 * u;
+        const uint32_t c = code[raw[u] & 0xFFu];
+        if (i < nb) dig[i] = (uint8_t)(METH ? (c >> 4) : (c & 3u));
+    }
+    __syncwarp();
+
+    // (5) ranks of this lane's 8 k-mers (src/seq.h:31-42 / :62-74).  They are visited in ROTATED order
+    // jj(j) = (j + lane/2) & 7 so that the 8-byte parameter stores of a half-warp fall into 16 different bank pairs.
+    const int rot = METH ? 0 : (lane >> 1);
+    uint32_t ranks[8];
+    {
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(dig + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(dig + m0 + 8);
+        if (!METH) {
+            // 16 two-bit digits packed first-digit-most-significant: ((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes
+            const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
+                               ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
+            const int sh0 = 32 - 2 * p.k;
+#pragma unroll
+            for (int j = 0; j < 8; j++) ranks[j] = (P >> (sh0 - 2 * ((j + rot) & 7))) & p.kmask;
+        } else {
+            const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
+            const int km1 = p.k - 1;
+            uint32_t rank = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < km1) rank = rank * 5 + ((dw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int bi = km1 + j;
+                const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
+                rank = (rank % p.kmask) * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);
+                ranks[j] = rank;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (m0 + ((j + rot) & 7) >= nk_tile) ranks[j] = 0;
+    }
+    float2 mv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) mv[j] = MODEL_SMEM ? model[ranks[j]] : __ldg(&model[ranks[j]]);
+
+    // (6) chunk -> k-mer map and boundary bitmap (needs only the dwells: runs while the gathers are in flight)
     if (RAND_DWELL) {
-        uint8_t *map = cs.map[team][buf];
-        uint8_t *bmap = cs.bmap[team][buf];
-        const uint32_t n16 = (((S + ph + 7) >> 3) + 15) >> 4;  // boundary bytes the consumers will read, in 16-byte units
-        for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(bmap)[i] = make_uint4(0, 0, 0, 0);
+        static_assert(MAPC / 16 <= 96, "three 16-byte stores per lane must cover the boundary bitmap");
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+            if (lane + 32 * u < MAPC / 16) reinterpret_cast<uint4 *>(bmap)[lane + 32 * u] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         if (active) {
             uint32_t oo = o;
@@ -569,141 +683,58 @@ __device__ __forceinline__ void produce_dwells(const GenParams &p, K4Shared &cs,
         for (int j = 0; j < 8; j++)
             if (m0 + j < nk_tile) p.ss[td.ss_pos + m0 + j] = d[j];
     }
-    if (lane == 0) {
-        int16_t *out = p.sig + sigoff;
-        TileHdr h;
-        h.S = S; h.ph = ph; h.B = B; h.L = L; h.r_lo = key.r_lo; h.r_hi = key.r_hi;
-        h.out_lo = (uint32_t)(uint64_t)out; h.out_hi = (uint32_t)((uint64_t)out >> 32);
-        cs.hdr[team][buf] = h;
-    }
-    __syncwarp();
-}
 
-// Producer warp 1: bases -> digits -> ranks (src/seq.h) -> (level_mean, level_stdv) gathers -> per-k-mer (A', B').
-// Source order = latency order: the byte loads and the gathers are issued as early as their inputs allow.
-template <bool NOISY, bool METH, bool MODEL_SMEM>
-__device__ __forceinline__ void produce_levels(const GenParams &p, K4Shared &cs, int team, int buf, const TileDesc td, int lane,
-                                               const float2 *__restrict__ model, unsigned long long *empty_bar,
-                                               uint32_t empty_parity) {
-    const int nk_tile = td.nk;
-    // the tile's base window: coalesced byte loads, all in flight at once
-    uint32_t raw[WIN_LOADS];
-    const int nb = nk_tile + p.k - 1;
-#pragma unroll
-    for (int u = 0; u < WIN_LOADS; u++) {
-        const int i = lane + 32 * u;
-        raw[u] = 0;
-        if (i < nb) raw[u] = __ldg(p.bases + (i < td.a_rem ? td.a_off : td.b_off) + i);
-    }
-    const double offset = __ldg(p.read_offset + td.read);
-    const int m0 = lane * 8;
-    const bool active = m0 < nk_tile;
-
-    // bases -> digits (the code table folds IUPAC letters, src/seq.h:14-28 / :45-60)
-    uint8_t *dig = cs.digit[team];
-#pragma unroll
-    for (int u = 0; u < WIN_LOADS; u++) {
-        const int i = lane + 32 * u;
-        const uint32_t code = cs.code[raw[u] & 0xFFu];
-        if (i < nb) dig[i] = (uint8_t)(METH ? (code >> 4) : (code & 3u));
-    }
-    __syncwarp();
-
-    // ranks of this lane's 8 k-mers (src/seq.h:31-42 / :62-74)
-    uint32_t ranks[8];
-    {
-        const uint2 dwa = *reinterpret_cast<const uint2 *>(dig + m0);
-        const uint2 dwb = *reinterpret_cast<const uint2 *>(dig + m0 + 8);
-        if (!METH) {
-            // 16 two-bit digits packed first-digit-most-significant: ((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes
-            const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
-                               ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
-            const int sh0 = 32 - 2 * p.k;
-#pragma unroll
-            for (int j = 0; j < 8; j++) ranks[j] = (P >> (sh0 - 2 * j)) & p.kmask;
-        } else {
-            const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
-            const int km1 = p.k - 1;
-            uint32_t rank = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i < km1) rank = rank * 5 + ((dw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int bi = km1 + j;
-                const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
-                rank = (rank % p.kmask) * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);
-                ranks[j] = rank;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (m0 + j >= nk_tile) ranks[j] = 0;
-    }
-    __syncwarp();  // every lane has read its digits: the staging area may be rewritten for the next tile
-    float2 mv[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) mv[j] = MODEL_SMEM ? model[ranks[j]] : __ldg(&model[ranks[j]]);
-
-    // per-k-mer parameters
-    float2 pr[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (NOISY) {
-            const float sd = __fmul_rn(mv[j].y, p.amp_noise);  // float product, src/sim.c:249
-            const double a = __dmul_rn((double)sd, p.scale);
-            const double b = __dsub_rn(__dmul_rn((double)mv[j].x, p.scale), offset);
-            pr[j] = make_float2((float)a, (float)b);
-        } else {
-            // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
-            const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
-            pr[j] = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
-        }
-    }
-    mbar_wait(empty_bar, empty_parity);
+    // (7) per-k-mer parameters from the gathered (level_mean, level_stdv)
     if (active) {
-        float2 *par = cs.par[team][buf] + m0;
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            // 16-byte stores: two k-mers at a time (rows beyond the tile are never read)
-            *reinterpret_cast<float4 *>(par + j) = make_float4(pr[j].x, pr[j].y, pr[j + 1].x, pr[j + 1].y);
+        for (int j = 0; j < 8; j++) {
+            float2 pr;
+            if (NOISY) {
+                const float sd = __fmul_rn(mv[j].y, p.amp_noise);  // float product, src/sim.c:249
+                const double a = __dmul_rn((double)sd, p.scale);
+                const double b = __dsub_rn(__dmul_rn((double)mv[j].x, p.scale), offset);
+                pr = make_float2((float)a, (float)b);
+            } else {
+                // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
+                const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
+                pr = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
+            }
+            par[m0 + ((j + rot) & 7)] = pr;  // rows beyond the tile are never read
         }
     }
     __syncwarp();
+    TileHdr h;
+    h.S = S; h.ph = ph; h.B = B; h.L = L; h.r_lo = key.r_lo; h.r_hi = key.r_hi;
+    h.out = p.sig + sigoff;
+    return h;
 }
 
-// dynamic shared memory: [K4Shared][Z16: 128 KB if USE_Z][model: num_kmer*8 B if MODEL_SMEM]
 template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
-__global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
+__global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
     constexpr bool USE_Z = NOISY || RAND_DWELL;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    K4Shared &cs = *reinterpret_cast<K4Shared *>(smem_raw);
-    __half *z16s = reinterpret_cast<__half *>(smem_raw + ((sizeof(K4Shared) + 127) & ~127u));
-    float2 *models = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(z16s) + (USE_Z ? Z16_N * 2 : 0));
+    extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
+    const int nw = blockDim.x >> 5;
     const int warp = tid >> 5, lane = tid & 31;
-    const int team = warp / TEAM_WARPS, role = warp % TEAM_WARPS;  // role 0 = producer
+    const K4Layout lay = k4_layout(nw, USE_Z, MODEL_SMEM ? p.num_kmer * 8 : 0);
+    uint4 *lut = reinterpret_cast<uint4 *>(smem + lay.lut);
+    uint8_t *code = smem + lay.code;
+    unsigned long long *stage_bar = reinterpret_cast<unsigned long long *>(smem + lay.mbar);
+    __half *z16s = reinterpret_cast<__half *>(smem + lay.z16);
+    float2 *models = reinterpret_cast<float2 *>(smem + lay.model);
 
-    // ---- prologue: tables and barriers ----
-    if (tid == 0) {
-        mbar_init(&cs.stage_bar, 1);
-        for (int t = 0; t < NTEAM; t++)
-            for (int b = 0; b < NBUF; b++) {
-                mbar_init(&cs.full[t][b], NPROD);
-                mbar_init(&cs.empty[t][b], NCONS);
-            }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    for (int i = tid; i < 256; i += K4_THREADS) cs.code[i] = base_code(i);
-    for (int i = tid; i < 128 * 8; i += K4_THREADS) {
-        const int m = (i >> 3) << 1;  // boundary mask (bit 0 is never used)
+    // ---- prologue: tables ----
+    if (tid == 0) mbar_init(stage_bar, 1);
+    for (int i = tid; i < 256; i += blockDim.x) code[i] = base_code(i);
+    for (int i = tid; i < 128 * LUT_COPIES; i += blockDim.x) {
+        const int m = (i / LUT_COPIES) << 1;  // boundary mask (bit 0 is never used)
         uint32_t f[8], cnt = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (j >= 1 && ((m >> j) & 1)) cnt++;
             f[j] = cnt * 8;
         }
-        cs.lut[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+        lut[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
     }
     __syncthreads();
     if (tid == 0) {
@@ -711,47 +742,33 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
         if (USE_Z) bytes += Z16_N * 2;
         if (MODEL_SMEM) bytes += p.num_kmer * 8;
         if (bytes) {
-            mbar_expect_tx(&cs.stage_bar, bytes);
+            mbar_expect_tx(stage_bar, bytes);
             if (USE_Z) {
-                tma_load_1d(z16s, p.z16, Z16_N, &cs.stage_bar);  // two 64 KB bulk copies
-                tma_load_1d(z16s + Z16_N / 2, p.z16 + Z16_N / 2, Z16_N, &cs.stage_bar);
+                tma_load_1d(z16s, p.z16, Z16_N, stage_bar);  // two 64 KB bulk copies
+                tma_load_1d(z16s + Z16_N / 2, p.z16 + Z16_N / 2, Z16_N, stage_bar);
             }
-            if (MODEL_SMEM) tma_load_1d(models, p.model, p.num_kmer * 8, &cs.stage_bar);
+            if (MODEL_SMEM) tma_load_1d(models, p.model, p.num_kmer * 8, stage_bar);
         }
     }
-    if (USE_Z || MODEL_SMEM) mbar_wait(&cs.stage_bar, 0);
-    if (smem_u32(&cs.par[NTEAM - 1][NBUF - 1][TK - 1]) + 64 >= 0x10000u) __trap();
+    if (USE_Z || MODEL_SMEM) mbar_wait(stage_bar, 0);
+    float2 *par = reinterpret_cast<float2 *>(smem + lay.par) + warp * TK;
+    uint8_t *map = smem + lay.map + warp * MAPC;
+    uint8_t *bmap = smem + lay.bmap + warp * MAPC;
+    uint8_t *dig = smem + lay.digit + warp * DIG_BYTES;
+    if (smem_u32(par) + TK * 8 + 64 >= 0x10000u) __trap();
+    const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
 
-    // ---- main loop: team-private tile sequence, NBUF-deep ring ----
-    const int gteam = blockIdx.x * NTEAM + team;
-    const int tstride = gridDim.x * NTEAM;
-    if (role < NPROD) {
-        const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
-        int it = 0;
-        TileDesc td_next = load_tile_desc(p.tiles, min(gteam, p.n_tiles - 1));
-        for (int tile = gteam; tile < p.n_tiles; tile += tstride, it++) {
-            const int buf = it % NBUF;
-            const uint32_t parity = (uint32_t)((it / NBUF) & 1);
-            const TileDesc td = td_next;
-            td_next = load_tile_desc(p.tiles, min(tile + tstride, p.n_tiles - 1));  // in flight during this tile
-            if (role == 0)
-                produce_dwells<RAND_DWELL, REV>(p, cs, team, buf, td, lane, z16s, &cs.empty[team][buf], parity ^ 1u);
-            else
-                produce_levels<NOISY, METH, MODEL_SMEM>(p, cs, team, buf, td, lane, model, &cs.empty[team][buf], parity ^ 1u);
-            if (lane == 0) mbar_arrive(&cs.full[team][buf]);
-        }
-    } else {
-        const int ctid = (role - NPROD) * 32 + lane;
-        int it = 0;
-        for (int tile = gteam; tile < p.n_tiles; tile += tstride, it++) {
-            const int buf = it % NBUF;
-            const uint32_t parity = (uint32_t)((it / NBUF) & 1);
-            mbar_wait(&cs.full[team][buf], parity);
-            const TileHdr h = cs.hdr[team][buf];
-            consume_tile<NOISY, RAND_DWELL, REV>(p, cs.par[team][buf], cs.map[team][buf], cs.bmap[team][buf], cs.lut, z16s, h, ctid);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cs.empty[team][buf]);
-        }
+    // ---- main loop: this warp's tiles ----
+    const int gwarp = blockIdx.x * nw + warp;
+    const int stride = gridDim.x * nw;
+    if (gwarp >= p.n_tiles) return;
+    TileDesc td_next = load_tile_desc(p.tiles, gwarp);
+    for (int tile = gwarp; tile < p.n_tiles; tile += stride) {
+        const TileDesc td = td_next;
+        td_next = load_tile_desc(p.tiles, min(tile + stride, p.n_tiles - 1));  // in flight during this tile
+        const TileHdr h = prepare_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, td, lane, par, map, bmap, dig, code, model, z16s);
+        emit_tile<NOISY, RAND_DWELL, REV>(p, par, map, bmap, lut, z16s, h, lane);
+        __syncwarp();  // the tile buffer is rewritten by the next prepare_tile
     }
 }
 
