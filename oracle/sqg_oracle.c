@@ -272,16 +272,17 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
         offset = sqo_lehmer_normal(&ls->offset, p->offset_mean, p->offset_std);
         median = sqo_lehmer_normal(&ls->median, p->median_before_mean, p->median_before_std);
     } else {
-        /* one Philox block per read; each deviate mixes two table normals 0.8*z1 + 0.6*z2 so that
-         * per-read values have 2^32 atoms (0.64 + 0.36 = 1 keeps unit variance) */
+        /* one Philox block per read; each deviate mixes two table normals cos(35deg)*z1 +
+         * sin(35deg)*z2 so that per-read values have ~2^30 atoms (unit variance; an irrational-looking ratio keeps
+         * sums of the binary16 table values from colliding) */
         uint32_t ctr[4] = {0, r_lo, r_hi, ST_READ}, w[4];
         sqo_philox4x32_10(ctr, o->key, w);
         double z[2];
         for (int d = 0; d < 2; d++) {
             float za = sqo_z16(o->zt, w[d] & 0xFFFFu, o->key, 2 * d, r_lo, r_hi, ST_READ_TAIL);
             float zb = sqo_z16(o->zt, w[d] >> 16, o->key, 2 * d + 1, r_lo, r_hi, ST_READ_TAIL);
-            double a = (double)za * 0.8;
-            double b = (double)zb * 0.6;
+            double a = (double)za * 0.8191520442889918;
+            double b = (double)zb * 0.573576436351046;
             z[d] = a + b;
         }
         double t0 = z[0] * p->offset_std;

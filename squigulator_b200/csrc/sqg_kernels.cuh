@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
         for (int d = 0; d < 2; d++) {
             const float za = z16(p.z16, p.z2, ww[d] & 0xFFFFu, 2 * d, key, ST_READ_TAIL);
             const float zb = z16(p.z16, p.z2, ww[d] >> 16, 2 * d + 1, key, ST_READ_TAIL);
-            z[d] = __dadd_rn(__dmul_rn((double)za, 0.8), __dmul_rn((double)zb, 0.6));
+            z[d] = __dadd_rn(__dmul_rn((double)za, 0.8191520442889918), __dmul_rn((double)zb, 0.573576436351046));
         }
         off = __dadd_rn(__dmul_rn(z[0], p.offset_std), p.offset_mean);
         med = __dadd_rn(__dmul_rn(z[1], p.median_std), p.median_mean);
