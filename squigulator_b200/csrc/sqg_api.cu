@@ -24,6 +24,7 @@
 
 #include "../../include/sqg.h"
 #include "sqg_kernels.cuh"
+#include "sqg_legacy.cuh"
 
 extern "C" const unsigned char sqg_ztable_blob[];  // Z16 (binary16) ++ Z2 (binary32), embedded from data/ztable_v2.bin (ztable_blob.S)
 
@@ -105,6 +106,10 @@ struct Slot {
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
     DevBuf<int32_t> d_ss;
+    // SQG_RNG_LEGACY scratch (per k-mer of the batch)
+    DevBuf<uint32_t> d_rank, d_rank_sorted, d_idx, d_idx_sorted;
+    DevBuf<uint64_t> d_dsorted, d_excl, d_heads, d_segstart, d_cpos;
+    DevBuf<unsigned char> d_cub;
     PinBuf<SegDesc> h_segs;
     PinBuf<ReadDesc> h_reads;
     PinBuf<int64_t> h_meta, h_sigoff, h_len64, h_ss_off;
@@ -121,6 +126,8 @@ struct Slot {
         d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release();
         d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
         d_offset.release(); d_median.release(); d_sig.release(); d_ss.release();
+        d_rank.release(); d_rank_sorted.release(); d_idx.release(); d_idx_sorted.release(); d_dsorted.release();
+        d_excl.release(); d_heads.release(); d_segstart.release(); d_cpos.release(); d_cub.release();
         h_segs.release(); h_reads.release(); h_meta.release(); h_sigoff.release(); h_len64.release();
         h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
         h_ss.release();
@@ -164,6 +171,10 @@ struct sqg_ctx {
     size_t k4_smem = 0;
     int k4_grid_per_sm = 1;
     int k4_warps = 16;
+    // SQG_RNG_LEGACY: positions reached in the reference's streams (src/sim.c:215-258, thread 0)
+    bool legacy = false;
+    uint64_t leg_dwell_pos = 0, leg_read_pos = 0;
+    DevBuf<uint64_t> d_cnt_kmer;
     std::atomic<int64_t> launches{0};
     Slot sync_slot;  // used by sqg_gen_batch / sqg_gen_sig
     // dispatcher
@@ -338,7 +349,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     CU(s.d_median.ensure(nr, false, s.stream));
     CU(s.d_meta.ensure(4, false, s.stream));
     CU(s.h_meta.ensure(4));
-    if (want & SQG_WANT_SS) CU(s.d_ss.ensure((size_t)std::max<int64_t>(nk_total, 1), false, s.stream));
+    if ((want & SQG_WANT_SS) || ctx->legacy) CU(s.d_ss.ensure((size_t)std::max<int64_t>(nk_total, 1), false, s.stream));
     return SQG_OK;
 }
 
@@ -355,23 +366,48 @@ GenParams slot_params(sqg_ctx *ctx, Slot &s) {
     return p;
 }
 
-// K1-K3: lengths and offsets.  Asynchronous on the slot's stream.
+LegacyParams legacy_params(sqg_ctx *ctx, Slot &s) {
+    LegacyParams q;
+    memset(&q, 0, sizeof q);
+    q.seed = ctx->cfg.seed;
+    q.dwell_pos0 = ctx->leg_dwell_pos;
+    q.read_pos0 = ctx->leg_read_pos;
+    q.cnt_kmer = ctx->d_cnt_kmer.p;
+    q.kmer_rank = s.d_rank.p;
+    q.kmer_cpos = s.d_cpos.p;
+    q.noisy = ctx->noisy; q.rand_dwell = ctx->rand_dwell; q.meth = ctx->meth; q.rev = ctx->rev;
+    q.dwell_mean = ctx->cfg.profile.dwell_mean; q.dwell_std = ctx->cfg.profile.dwell_std;
+    return q;
+}
+
+// K0-K3: tile descriptors, lengths and offsets.  Asynchronous on the slot's stream.
 int slot_plan(sqg_ctx *ctx, Slot &s) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
     CU(cudaMemsetAsync(s.d_meta.p, 0, 4 * sizeof(int64_t), s.stream));
     tile_desc_kernel<<<(int)((s.n_segs + 255) / 256), 256, 0, s.stream>>>(p);
     ctx->launches++;
-    if (ctx->rand_dwell) {
-        const int tiles_per_cta = K1_THREADS / 32;
-        dwell_sum_kernel<<<(int)((s.n_tiles + tiles_per_cta - 1) / tiles_per_cta), K1_THREADS, 0, s.stream>>>(p);
+    const int g2 = (int)((s.n_reads + 255) / 256);
+    const int tiles_per_cta = K1_THREADS / 32;
+    const int g1 = (int)((s.n_tiles + tiles_per_cta - 1) / tiles_per_cta);
+    if (ctx->legacy) {
+        const LegacyParams q = legacy_params(ctx, s);
+        legacy_dwell_kernel<<<g1, 128, 0, s.stream>>>(p, q);
+        read_plan_kernel<true><<<g2, 256, 0, s.stream>>>(p);
+        legacy_read_draws_kernel<<<g2, 256, 0, s.stream>>>(p, q);
+        ctx->launches += 3;
+    } else {
+        if (ctx->rand_dwell) {
+            dwell_sum_kernel<<<g1, K1_THREADS, 0, s.stream>>>(p);
+            ctx->launches++;
+            read_plan_kernel<true><<<g2, 256, 0, s.stream>>>(p);
+        } else {
+            read_plan_kernel<false><<<g2, 256, 0, s.stream>>>(p);
+        }
         ctx->launches++;
     }
-    const int g2 = (int)((s.n_reads + 255) / 256);
-    if (ctx->rand_dwell) read_plan_kernel<true><<<g2, 256, 0, s.stream>>>(p);
-    else read_plan_kernel<false><<<g2, 256, 0, s.stream>>>(p);
     read_offsets_kernel<<<1, 1024, 0, s.stream>>>(p);
-    ctx->launches += 2;
+    ctx->launches++;
     CU(cudaGetLastError());
     return SQG_OK;
 }
@@ -388,9 +424,58 @@ int slot_size_arena(sqg_ctx *ctx, Slot &s) {
     return SQG_OK;
 }
 
+// SQG_RNG_LEGACY signal generation: stream positions by sort + segmented scan, then the legacy sample kernel
+int slot_generate_legacy(sqg_ctx *ctx, Slot &s) {
+    const int64_t n = s.total_kmers;
+    const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    CU(s.d_rank.ensure(nn, false, s.stream)); CU(s.d_rank_sorted.ensure(nn, false, s.stream));
+    CU(s.d_idx.ensure(nn, false, s.stream)); CU(s.d_idx_sorted.ensure(nn, false, s.stream));
+    CU(s.d_dsorted.ensure(nn, false, s.stream)); CU(s.d_excl.ensure(nn, false, s.stream));
+    CU(s.d_heads.ensure(nn, false, s.stream)); CU(s.d_segstart.ensure(nn, false, s.stream));
+    CU(s.d_cpos.ensure(nn, false, s.stream));
+    const GenParams p = slot_params(ctx, s);
+    const LegacyParams q = legacy_params(ctx, s);
+    const int gb = (int)((n + 255) / 256);
+    legacy_rank_kernel<<<(int)s.n_tiles, 256, 0, s.stream>>>(p, q);
+    ctx->launches++;
+    if (ctx->noisy && n > 0) {
+        if (n > 0xFFFFFFF0ll) return fail(ctx, SQG_ERR_ARG, "legacy mode: batch too large");
+        legacy_iota_kernel<<<gb, 256, 0, s.stream>>>(s.d_idx.p, n);
+        int bits = 1;
+        while ((1ull << bits) < ctx->cfg.num_kmer) bits++;
+        size_t t1 = 0, t2 = 0, t3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t1, s.d_rank.p, s.d_rank_sorted.p, s.d_idx.p, s.d_idx_sorted.p, (int)n, 0, bits, s.stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, t2, s.d_dsorted.p, s.d_excl.p, (int)n, s.stream);
+        cub::DeviceScan::InclusiveScan(nullptr, t3, s.d_heads.p, s.d_segstart.p, cub::Max(), (int)n, s.stream);
+        size_t tb = std::max(t1, std::max(t2, t3));
+        CU(s.d_cub.ensure(tb + 16, false, s.stream));
+        CU(cub::DeviceRadixSort::SortPairs(s.d_cub.p, tb, s.d_rank.p, s.d_rank_sorted.p, s.d_idx.p, s.d_idx_sorted.p, (int)n, 0, bits, s.stream));
+        legacy_gather_dwell_kernel<<<gb, 256, 0, s.stream>>>(s.d_ss.p, s.d_idx_sorted.p, s.d_dsorted.p, n);
+        CU(cub::DeviceScan::ExclusiveSum(s.d_cub.p, tb, s.d_dsorted.p, s.d_excl.p, (int)n, s.stream));
+        legacy_heads_kernel<<<gb, 256, 0, s.stream>>>(s.d_rank_sorted.p, s.d_excl.p, s.d_heads.p, n);
+        CU(cub::DeviceScan::InclusiveScan(s.d_cub.p, tb, s.d_heads.p, s.d_segstart.p, cub::Max(), (int)n, s.stream));
+        legacy_cpos_kernel<<<gb, 256, 0, s.stream>>>(s.d_rank_sorted.p, s.d_idx_sorted.p, s.d_excl.p, s.d_segstart.p, ctx->d_cnt_kmer.p, s.d_cpos.p, n);
+        legacy_carry_kernel<<<gb, 256, 0, s.stream>>>(s.d_rank_sorted.p, s.d_excl.p, s.d_segstart.p, s.d_dsorted.p, ctx->d_cnt_kmer.p, n);
+        ctx->launches += 9;
+    }
+    const int g1 = (int)((s.n_tiles + 3) / 4);
+    legacy_signal_kernel<<<g1, 128, 0, s.stream>>>(p, q);
+    ctx->launches++;
+    if (ctx->prefix && ctx->rev) {
+        prefix_shift_kernel<<<(int)s.n_reads, 256, 0, s.stream>>>(p);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    // the streams have moved on (reference: state persists across reads, src/sim.c:215-258)
+    if (ctx->rand_dwell) ctx->leg_dwell_pos += (uint64_t)n;
+    if (!(ctx->cfg.flags & SQG_IDEAL)) ctx->leg_read_pos += (uint64_t)s.n_reads;
+    return SQG_OK;
+}
+
 // K4 (+ the RNA prefix shift).  Asynchronous.
 int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr) {
     if (s.n_reads == 0) return SQG_OK;
+    if (ctx->legacy) return slot_generate_legacy(ctx, s);
     const GenParams p = slot_params(ctx, s);
     const int grid = (int)std::min<int64_t>((s.n_tiles + ctx->k4_warps - 1) / ctx->k4_warps, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
@@ -485,7 +570,8 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
     if (!(pr.range > 0) || !(pr.digitisation > 0) || !(pr.dwell_mean >= 1) || pr.dwell_std < 0)
         return fail(ctx, SQG_ERR_ARG, "profile: need range>0, digitisation>0, dwell_mean>=1, dwell_std>=0");
     if (cfg->rng_mode != SQG_RNG_PHILOX && cfg->rng_mode != SQG_RNG_LEGACY) return fail(ctx, SQG_ERR_ARG, "unknown rng_mode");
-    if (cfg->rng_mode == SQG_RNG_LEGACY) return fail(ctx, SQG_ERR_ARG, "SQG_RNG_LEGACY is not available in this build");
+    ctx->legacy = cfg->rng_mode == SQG_RNG_LEGACY;
+    if (ctx->legacy && cfg->seed < 1) return fail(ctx, SQG_ERR_ARG, "SQG_RNG_LEGACY needs seed >= 1");
 
     const bool ideal = cfg->flags & SQG_IDEAL;
     ctx->noisy = !(ideal || (cfg->flags & SQG_IDEAL_AMP));
@@ -567,6 +653,10 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     const size_t zbytes = (size_t)Z16_N * 2 + 16 * Z2_SUB * sizeof(float);
     CU(ctx->d_z.ensure(zbytes));
     CU(cudaMemcpy(ctx->d_z.p, sqg_ztable_blob, zbytes, cudaMemcpyHostToDevice));
+    if (ctx->legacy) {
+        CU(ctx->d_cnt_kmer.ensure(n));
+        CU(cudaMemset(ctx->d_cnt_kmer.p, 0, n * sizeof(uint64_t)));
+    }
     ctx->base.model = ctx->d_model.p;
     ctx->base.z16 = reinterpret_cast<const __half *>(ctx->d_z.p);
     ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z16_N * 2);
@@ -615,7 +705,8 @@ int init_common(sqg_ctx **out, const sqg_config_t *cfg, const sqg_model_t *h_mod
 
 int ensure_dispatcher(sqg_ctx *ctx) {
     if (!ctx->slots.empty()) return SQG_OK;
-    const int n = ctx->cfg.n_slots > 0 ? std::min(ctx->cfg.n_slots, 16) : 3;
+    // legacy streams are consumed in submission order: one slot, one worker
+    const int n = ctx->legacy ? 1 : (ctx->cfg.n_slots > 0 ? std::min(ctx->cfg.n_slots, 16) : 3);
     ctx->slots.resize(n);
     ctx->queues.resize(n);
     ctx->slot_busy.assign(n, 0);
@@ -658,6 +749,7 @@ void sqg_destroy(sqg_ctx_t *ctx) {
     ctx->sync_slot.release();
     ctx->d_model.release();
     ctx->d_z.release();
+    ctx->d_cnt_kmer.release();
     delete ctx;
 }
 
