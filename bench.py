@@ -153,7 +153,8 @@ def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    reads_per_step = args.cpu_reads if args.cpu_reads else max(cores * 40, 64)
+    # ~2 s of CPU work per step so that a --steps 50 run still ends within a few minutes
+    reads_per_step = args.cpu_reads if args.cpu_reads else max(cores * 200, 64)
     bases, off = synth_reads(reads_per_step, args.read_len, wl["rna"], seed=1234)
     times, samples = [], 0
     for i in range(args.warmup + args.steps):
@@ -228,8 +229,15 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
     peak, how = measured_peak()
     alg_bytes = 2.0 * info["samples"] + 1.0 * info["kmers"]
     k4_ms = ms_k4 / steps
+    # DRAM traffic of one launch from the committed ncu --set full capture of this very configuration, else null
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_signal_kernel_ncu.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        if t.get("workload") == wl["profile"] and t.get("reads_per_step") == n_reads and t.get("samples") == info["samples"]:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     out["roofline"] = {"bound": "hbm", "kernel": "signal_kernel", "achieved": alg_bytes / (k4_ms * 1e-3) / 1e9, "peak": peak,
-                       "unit": "GB/s", "frac": alg_bytes / (k4_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                       "unit": "GB/s", "frac": alg_bytes / (k4_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                        "peak_source": how, "kernel_ms": k4_ms, "kernel_share_of_step": ms_k4 / ms_total,
                        "algorithmic_bytes_per_launch": alg_bytes}
     gen.dev_batch_destroy(db)
@@ -352,7 +360,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_extra:
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_reads if args.cpu_reads else max(cores * 40, 64)
+        n_cpu = args.cpu_reads if args.cpu_reads else max(cores * 1400, 64)  # ~10-20 s of gen_sig on all cores
         cb, co = synth_reads(n_cpu, args.read_len, wl["rna"], seed=1234)
         r = cpu_reference_run(wl, cb, co, seed=1)
         cpu = {"value": r["samples"] / r["seconds"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],

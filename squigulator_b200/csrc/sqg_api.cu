@@ -23,6 +23,8 @@
 #include <vector>
 
 #include "../../include/sqg.h"
+#include <cuda/functional>
+
 #include "sqg_kernels.cuh"
 #include "sqg_legacy.cuh"
 
@@ -446,14 +448,14 @@ int slot_generate_legacy(sqg_ctx *ctx, Slot &s) {
         size_t t1 = 0, t2 = 0, t3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, t1, s.d_rank.p, s.d_rank_sorted.p, s.d_idx.p, s.d_idx_sorted.p, (int)n, 0, bits, s.stream);
         cub::DeviceScan::ExclusiveSum(nullptr, t2, s.d_dsorted.p, s.d_excl.p, (int)n, s.stream);
-        cub::DeviceScan::InclusiveScan(nullptr, t3, s.d_heads.p, s.d_segstart.p, cub::Max(), (int)n, s.stream);
+        cub::DeviceScan::InclusiveScan(nullptr, t3, s.d_heads.p, s.d_segstart.p, cuda::maximum<uint64_t>{}, (int)n, s.stream);
         size_t tb = std::max(t1, std::max(t2, t3));
         CU(s.d_cub.ensure(tb + 16, false, s.stream));
         CU(cub::DeviceRadixSort::SortPairs(s.d_cub.p, tb, s.d_rank.p, s.d_rank_sorted.p, s.d_idx.p, s.d_idx_sorted.p, (int)n, 0, bits, s.stream));
         legacy_gather_dwell_kernel<<<gb, 256, 0, s.stream>>>(s.d_ss.p, s.d_idx_sorted.p, s.d_dsorted.p, n);
         CU(cub::DeviceScan::ExclusiveSum(s.d_cub.p, tb, s.d_dsorted.p, s.d_excl.p, (int)n, s.stream));
         legacy_heads_kernel<<<gb, 256, 0, s.stream>>>(s.d_rank_sorted.p, s.d_excl.p, s.d_heads.p, n);
-        CU(cub::DeviceScan::InclusiveScan(s.d_cub.p, tb, s.d_heads.p, s.d_segstart.p, cub::Max(), (int)n, s.stream));
+        CU(cub::DeviceScan::InclusiveScan(s.d_cub.p, tb, s.d_heads.p, s.d_segstart.p, cuda::maximum<uint64_t>{}, (int)n, s.stream));
         legacy_cpos_kernel<<<gb, 256, 0, s.stream>>>(s.d_rank_sorted.p, s.d_idx_sorted.p, s.d_excl.p, s.d_segstart.p, ctx->d_cnt_kmer.p, s.d_cpos.p, n);
         legacy_carry_kernel<<<gb, 256, 0, s.stream>>>(s.d_rank_sorted.p, s.d_excl.p, s.d_segstart.p, s.d_dsorted.p, ctx->d_cnt_kmer.p, n);
         ctx->launches += 9;
