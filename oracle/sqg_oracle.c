@@ -147,9 +147,13 @@ float sqo_z16(const void *zt, uint32_t h, const uint32_t key[2], uint32_t c0, ui
  * among 2^11 cells spread evenly over the whole table, and every table cell is used by some block residue. */
 static uint32_t stratify(uint32_t h, uint32_t block) { return (h & 0xFFC1u) | ((block & 31u) << 1); }
 
-static uint32_t halfword(const uint32_t w[4], uint32_t j) { /* j in 0..7 */
+/* the j-th 16-bit draw (j in 0..7) of a Philox block: even draws are bits 1..16 of word j/2, odd draws bits 1..16
+ * of the same word rotated by 16 (i.e. bits 17..31 and 0).  The two draws of a word share no bit that survives
+ * stratify(), and on the GPU `word & 0x1FF82` is directly the byte offset of the table entry. */
+static uint32_t halfword(const uint32_t w[4], uint32_t j) {
     uint32_t x = w[j >> 1];
-    return (j & 1) ? (x >> 16) : (x & 0xFFFFu);
+    if (j & 1) x = (x >> 16) | (x << 16);
+    return (x >> 1) & 0xFFFFu;
 }
 
 /* ------------------------------------------------------------------ handle */

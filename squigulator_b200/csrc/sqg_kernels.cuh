@@ -102,10 +102,16 @@ __device__ __forceinline__ RngKey make_key(const GenParams &p, int read_local) {
     return RngKey{p.key0, p.key1, (uint32_t)r, (uint32_t)(r >> 32)};
 }
 
-__device__ __forceinline__ uint32_t halfword(const uint4 &w, int j) {  // j in 0..7, compile-time after unrolling
+// the j-th 16-bit draw (j in 0..7) of a Philox block: even draws are bits 1..16 of word j/2, odd draws bits 1..16 of
+// the same word rotated by 16.  Defined this way so that `word & 0x1FF82` is already the BYTE offset of the stratified
+// table entry (bit 0 of a binary16 offset is 0, bits 2-6 are the bank): no shift, no multiply in the sample loop.
+__device__ __forceinline__ uint32_t draw_word(const uint4 &w, int j) {  // j compile-time after unrolling
     const uint32_t x = (j >> 1) == 0 ? w.x : (j >> 1) == 1 ? w.y : (j >> 1) == 2 ? w.z : w.w;
-    return (j & 1) ? (x >> 16) : (x & 0xFFFFu);
+    return (j & 1) ? __byte_perm(x, x, 0x1032) : x;  // rotate by 16
 }
+__device__ __forceinline__ uint32_t halfword(const uint4 &w, int j) { return (draw_word(w, j) >> 1) & 0xFFFFu; }
+// byte offset of the stratified table entry of a draw: ((h & 0xFFC1) | bank<<1) * 2
+__device__ __forceinline__ uint32_t draw_offset(uint32_t word, uint32_t bank4) { return (word & 0x1FF82u) | bank4; }
 
 // n / sps_fixed for tile-local sample numbers (exact: see GenParams::sps_magic)
 __device__ __forceinline__ uint32_t div_sps(const GenParams &p, uint32_t n) {
@@ -400,8 +406,9 @@ __device__ __noinline__ void slow_chunk(const GenParams &p, const float2 *par, c
         const float2 ab = par[k];
         uint32_t v;
         if (NOISY) {
-            const uint32_t x = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
-            const uint32_t hw = stratify((e & 1) ? (x >> 16) : (x & 0xFFFFu), q0 >> 3);
+            uint32_t x = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
+            if (e & 1) x = __byte_perm(x, x, 0x1032);
+            const uint32_t hw = stratify((x >> 1) & 0xFFFFu, q0 >> 3);
             const float z = z16(z16s, p.z2, hw, q0 + e, key, ST_AMP_TAIL);
             v = to_i16_bits(fmaf(z, ab.x, ab.y));
         } else {
@@ -448,13 +455,13 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float
         float zmax = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-            const uint32_t bank = ((q0[c] >> 3) & 31u) << 1;  // stratify(): the chunk's Philox block picks the bank
+            const uint32_t bank4 = ((q0[c] >> 3) & 31u) << 2;  // stratify(): the chunk's Philox block picks the bank
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
                 const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
-                const uint32_t hw = (((e & 1) ? (rw[c][e >> 1] >> 16) : rw[c][e >> 1]) & 0xFFC1u) | bank;
-                const float z = lds_half(zbase + 2u * hw);
+                const uint32_t x = (e & 1) ? __byte_perm(rw[c][e >> 1], rw[c][e >> 1], 0x1032) : rw[c][e >> 1];
+                const float z = lds_half(zbase + draw_offset(x, bank4));
                 zmax = fmaxf(zmax, fabsf(z));
                 v[c][e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
             }
@@ -464,11 +471,12 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float
             const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
-                const uint32_t bank = ((q0[c] >> 3) & 31u) << 1;
+                const uint32_t bank4 = ((q0[c] >> 3) & 31u) << 2;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int e = REV ? 7 - j : j;
-                    const uint32_t hw = (((e & 1) ? (rw[c][e >> 1] >> 16) : rw[c][e >> 1]) & 0xFFC1u) | bank;
+                    const uint32_t x = (e & 1) ? __byte_perm(rw[c][e >> 1], rw[c][e >> 1], 0x1032) : rw[c][e >> 1];
+                    const uint32_t hw = draw_offset(x, bank4) >> 1;
                     if ((hw & 0x7FFFu) >= Z_TAIL_FIRST) {
                         const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
                         const float z = z16_tail(p.z2, hw, q0[c] + e, key, ST_AMP_TAIL);
@@ -574,7 +582,7 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
         float zmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float z = lds_half(zbase + 2u * stratify(halfword(w, j), blk));
+            const float z = lds_half(zbase + draw_offset(draw_word(w, j), (blk & 31u) << 2));
             zmax = fmaxf(zmax, fabsf(z));
             d[j] = dwell_from_z(z, p.dwell_mean, p.dwell_std);
         }
