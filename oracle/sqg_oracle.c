@@ -99,8 +99,8 @@ void sqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 enum { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
 
 #define Z16_N 65536
-#define Z_TAIL_FIRST 32752
-#define Z2_SUB 1024
+#define Z_TAIL_FIRST 32766
+#define Z2_SUB 8192
 
 /* IEEE binary16 -> binary32, exact */
 static float half_to_float(uint16_t h) {
@@ -123,8 +123,8 @@ static float half_to_float(uint16_t h) {
     return f;
 }
 
-/* 16-bit uniform -> N(0,1) by quantile table (bit 15 = sign, bits 0-14 = half-normal cell); the 16
- * outermost cells take 10 more bits from a dedicated Philox block addressed by (c0,c1,c2,tail_stream).
+/* 16-bit uniform -> N(0,1) by quantile table (bit 15 = sign, bits 0-14 = half-normal cell); the 2
+ * outermost cells take 13 more bits from a dedicated Philox block addressed by (c0,c1,c2,tail_stream).
  * zt = the bytes of squigulator_b200/data/ztable_v2.bin: Z16[65536] binary16, then Z2[16384] binary32.
  * DESIGN.md "z16". */
 float sqo_z16(const void *zt, uint32_t h, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,

@@ -8,11 +8,11 @@ The Philox path turns one 16-bit uniform h into a standard normal deviate by tab
     z = +-Z1[i],  Z1[i] = sqrt(E[z^2 | a_i <= z < b_i])          (the cell's conditional RMS)
 
 so every cell has probability 2^-16 and the discrete law has mean 0 and variance EXACTLY 1
-(sum_i 2^-15 * Z1[i]^2 = E[z^2] = 1).  The 16 outermost cells (i >= 32752, z > 3.49 sigma,
-probability 2^-11) are refined once more with 10 fresh bits: sub-cell j of tail cell t=i-32752 is
-[ndtri(0.5 + (i + j/1024)/65536), ndtri(0.5 + (i + (j+1)/1024)/65536)) with representative
-Z2[t*1024+j] = conditional RMS again, which keeps the variance exact and extends the support to
-~5.8 sigma (the reference's Box-Muller on a 31-bit Lehmer uniform reaches 6.55 sigma,
+(sum_i 2^-15 * Z1[i]^2 = E[z^2] = 1).  The 2 outermost cells (i >= 32766, z > 4.0 sigma,
+probability 2^-14) are refined once more with 13 fresh bits: sub-cell j of tail cell t=i-32766 is
+[ndtri(0.5 + (i + j/8192)/65536), ndtri(0.5 + (i + (j+1)/8192)/65536)) with representative
+Z2[t*8192+j] = conditional RMS again, which keeps the variance exact and extends the support to
+~6.2 sigma (the reference's Box-Muller on a 31-bit Lehmer uniform reaches 6.55 sigma,
 /root/reference src/rand.h:79-94).
 
 Output: squigulator_b200/data/ztable_v2.bin =
@@ -30,8 +30,8 @@ import numpy as np
 from scipy.special import ndtri, ndtr
 
 N1 = 32768
-TAIL_CELLS = 16
-SUB = 1024
+TAIL_CELLS = 2
+SUB = 8192
 
 
 def cond_rms(a, b):

@@ -618,7 +618,7 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
     if (ctx->rand_dwell) {
         // largest possible dwell: |z| <= Z_MAX, folded values included
         const double mx = std::floor((double)b.dwell_mean + (double)Z_MAX * (double)b.dwell_std + 0.5) + 2.0;
-        if (!(mx < 1200.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 5.72*dwell_std too large for one tile");
+        if (!(mx < 1200.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 6.06*dwell_std too large for one tile");
         int T = (int)((MAPC * 8 - 16) / (int)mx) & ~7;
         b.T = std::max(8, std::min(T, TK));
     } else {
@@ -652,7 +652,7 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     CU(ctx->d_model.ensure(n));
     if (h_model) CU(cudaMemcpy(ctx->d_model.p, h_model, n * sizeof(float2), cudaMemcpyHostToDevice));
     else CU(cudaMemcpy(ctx->d_model.p, d_model_in, n * sizeof(float2), cudaMemcpyDeviceToDevice));
-    const size_t zbytes = (size_t)Z16_N * 2 + 16 * Z2_SUB * sizeof(float);
+    const size_t zbytes = (size_t)Z16_N * 2 + Z2_N * sizeof(float);
     CU(ctx->d_z.ensure(zbytes));
     CU(cudaMemcpy(ctx->d_z.p, sqg_ztable_blob, zbytes, cudaMemcpyHostToDevice));
     if (ctx->legacy) {
@@ -676,6 +676,7 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     if (lay.total > smem_max || lay.par + (uint32_t)nw * TK * 8 + 2048 >= 0x10000u)
         return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
     ctx->k4_warps = nw;
+    ctx->base.lay = lay;
     ctx->k4_smem = lay.total;
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
     CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));

@@ -45,10 +45,11 @@ __device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint
 enum : uint32_t { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
 
 constexpr int Z16_N = 65536;          // Z16[h]: bit 15 of h = sign, bits 0-14 = half-normal cell of probability 2^-16
-constexpr int Z_TAIL_FIRST = 32752;   // the 16 outermost cells are refined ...
-constexpr int Z2_SUB = 1024;          // ... into 1024 sub-cells each (Z2, float32)
-constexpr float Z_MAX = 5.7152314f;   // largest table entry (bounds the dwell per k-mer)
-constexpr float Z_TAIL_THR = 3.49609375f;  // fp16(Z1[32752]): |z| >= this <=> possibly a tail cell
+constexpr int Z_TAIL_FIRST = 32766;   // the 2 outermost cells (p = 2^-14) are refined ...
+constexpr int Z2_SUB = 8192;          // ... into 8192 sub-cells each (Z2, float32)
+constexpr int Z2_N = 2 * Z2_SUB;
+constexpr float Z_MAX = 6.0590086f;   // largest table entry (bounds the dwell per k-mer)
+constexpr float Z_TAIL_THR = 4.08203125f;  // fp16(Z1[32766]): |z| >= this <=> possibly a tail cell
 
 struct RngKey {
     uint32_t k0, k1;       // Philox key = seed
@@ -61,7 +62,7 @@ struct RngKey {
 // picks uniformly among 2^11 cells spread evenly over the table, and all cells are used across block residues.
 __device__ __forceinline__ uint32_t stratify(uint32_t h, uint32_t block) { return (h & 0xFFC1u) | ((block & 31u) << 1); }
 
-// rare path of z16: 10 fresh bits pick the sub-cell
+// rare path of z16: 13 fresh bits pick the sub-cell
 __device__ __noinline__ float z16_tail(const float *__restrict__ z2g, uint32_t h, uint32_t c0, RngKey key,
                                        uint32_t stream) {
     const uint4 w = philox4x32_10(c0, key.r_lo, key.r_hi, stream, key.k0, key.k1);

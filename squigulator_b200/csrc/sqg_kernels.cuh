@@ -50,6 +50,12 @@ struct __align__(16) TileDesc {
     uint32_t pad;
 };
 
+// Shared-memory layout of the signal kernel (byte offsets into dynamic shared memory; computed on the host by
+// k4_layout() and passed in the kernel parameters, i.e. the constant bank)
+struct K4Layout {
+    uint32_t par, map, bmap, digit, lut, code, mbar, z16, model, total;
+};
+
 struct GenParams {
     // inputs
     const uint8_t *bases;
@@ -57,7 +63,7 @@ struct GenParams {
     const ReadDesc *reads;
     const float2 *model;  // (level_mean, level_stdv) by rank
     const __half *z16;    // Z16[65536]
-    const float *z2;      // Z2[16*1024]
+    const float *z2;      // Z2[2*8192]
     // plan (written by K0-K3, read by K4)
     TileDesc *tiles;
     uint32_t *tile_sum;
@@ -90,6 +96,7 @@ struct GenParams {
     int64_t first_read;
     int32_t want_ss;
     int32_t shift_val;  // (int16)(30*digitisation/range)
+    K4Layout lay;       // shared-memory layout of the signal kernel for the launch's warp count
 };
 
 constexpr int K1_THREADS = 128;  // 4 tiles per CTA, one warp each
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
 constexpr int K4_MAX_WARPS = 24;
 constexpr int K4_MAX_THREADS = K4_MAX_WARPS * 32;  // register budget: 65536 / 768 = 85
 constexpr int TK = 256;      // k-mers per tile (32 lanes x 8)
-constexpr int MAPC = 1280;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8
+constexpr int MAPC = 1344;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8 (dna-r10: 256 k-mers x 40)
 constexpr int DIG_BYTES = TK + 32;
 constexpr int LUT_COPIES = 4;
 constexpr int NCHUNK = 1;    // 16-byte chunks per lane per phase-B iteration (more = more ILP but more code)
@@ -301,9 +308,6 @@ constexpr int WARP_TILE_BYTES = TK * 8 + 2 * MAPC + DIG_BYTES;  // par + map + b
 //   [par: nw*TK float2]  (first, so that parameter addresses fit 16 bits)   [map: nw*MAPC u8] [bmap: nw*MAPC u8]
 //   [digit: nw*DIG_BYTES u8] [lut: 128*LUT_COPIES uint4] [code: 256 u8] [mbar: 8 B, 16-aligned]
 //   [Z16: 128 KB, 128-aligned, if USE_Z] [model: num_kmer*8 B if MODEL_SMEM]
-struct K4Layout {
-    uint32_t par, map, bmap, digit, lut, code, mbar, z16, model, total;
-};
 __host__ __device__ inline K4Layout k4_layout(int nw, bool use_z, uint32_t model_bytes) {
     K4Layout L;
     uint32_t o = 0;
@@ -328,6 +332,16 @@ __device__ __forceinline__ float lds_half(uint32_t addr) {
     unsigned short h;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
     return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     float2 v;
@@ -418,14 +432,18 @@ __device__ __noinline__ void slow_chunk(const GenParams &p, const float2 *par, c
     }
 }
 
+// 32-bit shared addresses of a warp's tile buffer and of the CTA's tables, computed once per kernel
+struct WarpSmem {
+    uint32_t par, map, bmap, lut, z;
+};
+
 // NCH chunks of the same lane (w, w+32, ...) in one straight-line block so that their Philox chains and table
 // lookups interleave (instruction-level parallelism: a warp alone sustains ~2x the issue rate).
 template <bool NOISY, bool RAND_DWELL, bool REV, int NCH>
-__device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
-                                                 const uint4 *lut, const __half *z16s, const TileHdr &h, int lane,
+__device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpSmem &ws, const TileHdr &h, int lane,
                                                  const uint32_t (&wv)[NCH], const bool (&st)[NCH]) {
-    const uint32_t zbase = smem_u32(z16s);
-    const uint32_t par_addr = smem_u32(par);  // < 64 KB by layout
+    const uint32_t zbase = ws.z;
+    const uint32_t par_addr = ws.par;  // < 64 KB by layout
     uint32_t q0[NCH], pa[NCH][4], v[NCH][8];
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
@@ -434,14 +452,14 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float
         q0[c] = REV ? (h.L - h.B - (s0 + 8)) : (h.B + s0);  // emitted position, multiple of 8
         uint32_t k0, bm;
         if (RAND_DWELL) {
-            k0 = map[wc];
-            bm = bmap[wc] >> 1;
+            k0 = lds_u8(ws.map + wc);
+            bm = lds_u8(ws.bmap + wc) >> 1;
         } else {
             k0 = div_sps(p, s0);
             bm = 0;
             for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << (b - 1);
         }
-        const uint4 lu = lut[bm * LUT_COPIES + (lane & (LUT_COPIES - 1))];
+        const uint4 lu = lds_u4(ws.lut + (bm * LUT_COPIES + (lane & (LUT_COPIES - 1))) * 16);
         const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
         pa[c][0] = lu.x + rep; pa[c][1] = lu.y + rep; pa[c][2] = lu.z + rep; pa[c][3] = lu.w + rep;
     }
@@ -467,7 +485,7 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float
             }
         }
         if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
-            // rare: some draw fell into one of the 16 outermost cells -> refine it (10 more bits)
+            // rare: some draw fell into one of the 16 outermost cells -> refine it (13 more bits)
             const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
@@ -505,8 +523,8 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const float
 }
 
 template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __forceinline__ void emit_tile(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
-                                          const uint4 *lut, const __half *z16s, const TileHdr h, int lane) {
+__device__ __forceinline__ void emit_tile(const GenParams &p, const WarpSmem &ws, const float2 *par, const uint8_t *map,
+                                          const uint8_t *bmap, const __half *z16s, const TileHdr h, int lane) {
     const uint32_t nW = (h.S + h.ph + 7) >> 3;
     // chunks [wlo, whi) lie fully inside the tile; chunk 0 is clipped iff ph > 0, the last one iff it overhangs S
     const uint32_t wlo = h.ph ? 1u : 0u;
@@ -519,7 +537,7 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const float2 *par,
             st[c] = w + 32u * c < whi;
             wv[c] = st[c] ? w + 32u * c : w;  // a missing partner is computed redundantly and not stored
         }
-        emit_chunks_fast<NOISY, RAND_DWELL, REV, NCHUNK>(p, par, map, bmap, lut, z16s, h, lane, wv, st);
+        emit_chunks_fast<NOISY, RAND_DWELL, REV, NCHUNK>(p, ws, h, lane, wv, st);
     }
     // the (at most two) clipped chunks at the ends of the tile: generic path, both in one warp-level call
     if (lane < 2) {
@@ -724,7 +742,7 @@ __global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_
     const int tid = threadIdx.x;
     const int nw = blockDim.x >> 5;
     const int warp = tid >> 5, lane = tid & 31;
-    const K4Layout lay = k4_layout(nw, USE_Z, MODEL_SMEM ? p.num_kmer * 8 : 0);
+    const K4Layout &lay = p.lay;
     uint4 *lut = reinterpret_cast<uint4 *>(smem + lay.lut);
     uint8_t *code = smem + lay.code;
     unsigned long long *stage_bar = reinterpret_cast<unsigned long long *>(smem + lay.mbar);
@@ -765,6 +783,7 @@ __global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_
     uint8_t *dig = smem + lay.digit + warp * DIG_BYTES;
     if (smem_u32(par) + TK * 8 + 64 >= 0x10000u) __trap();
     const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
+    const WarpSmem ws{smem_u32(par), smem_u32(map), smem_u32(bmap), smem_u32(lut), smem_u32(z16s)};
 
     // ---- main loop: this warp's tiles ----
     const int gwarp = blockIdx.x * nw + warp;
@@ -775,7 +794,7 @@ __global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_
         const TileDesc td = td_next;
         td_next = load_tile_desc(p.tiles, min(tile + stride, p.n_tiles - 1));  // in flight during this tile
         const TileHdr h = prepare_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, td, lane, par, map, bmap, dig, code, model, z16s);
-        emit_tile<NOISY, RAND_DWELL, REV>(p, par, map, bmap, lut, z16s, h, lane);
+        emit_tile<NOISY, RAND_DWELL, REV>(p, ws, par, map, bmap, z16s, h, lane);
         __syncwarp();  // the tile buffer is rewritten by the next prepare_tile
     }
 }

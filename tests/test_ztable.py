@@ -15,18 +15,18 @@ def tables():
 
 def test_layout_and_symmetry(tables):
     z16, z2 = tables
-    assert z16.size == 65536 and z2.size == 16 * 1024
+    assert z16.size == 65536 and z2.size == 2 * 8192
     assert np.array_equal(z16[32768:], -z16[:32768])           # bit 15 of the index is the sign
     assert np.all(np.diff(z16[:32768]) >= 0) and z16[0] > 0     # monotone half-normal quantiles
     assert np.all(np.diff(z2) > 0)
-    assert float(z16[32752]) == 3.49609375                      # Z_TAIL_THR in sqg_device.cuh
-    assert abs(float(z2[-1]) - 5.7152314) < 1e-6                # Z_MAX in sqg_device.cuh
+    assert float(z16[32766]) == 4.08203125                      # Z_TAIL_THR in sqg_device.cuh
+    assert abs(float(z2[-1]) - 6.0590086) < 1e-6                # Z_MAX in sqg_device.cuh
 
 
 def test_unit_variance(tables):
     z16, z2 = tables
-    body = (z16[:32752] ** 2).sum() / 32768
-    tail = (z2 ** 2).sum() / (32768 * 1024)
+    body = (z16[:32766] ** 2).sum() / 32768
+    tail = (z2 ** 2).sum() / (32768 * 8192)
     assert abs(body + tail - 1.0) < 5e-6      # two-level law, incl. the fp16 rounding of the body
     assert abs((z16[:32768] ** 2).mean() - 1.0) < 5e-6
 
@@ -44,17 +44,17 @@ def test_cells_match_mpmath(tables):
         den = mp.quad(lambda z: mp.npdf(z), [a, b])
         return float(mp.sqrt(num / den))
 
-    for i in (0, 7, 1000, 16384, 30000, 32751):
+    for i in (0, 7, 1000, 16384, 30000, 32765):
         a = edge(mp.mpf(1) / 2 + mp.mpf(i) / 65536)
         b = edge(mp.mpf(1) / 2 + mp.mpf(i + 1) / 65536)
         r = rms(a, b)
         assert abs(float(np.float16(r)) - z16[i]) <= abs(r) * 2 ** -10, i   # same value up to one fp16 ulp
-    for t, j in ((0, 0), (5, 512), (15, 1022)):
-        i = 32752 + t
-        a = edge(mp.mpf(1) / 2 + (mp.mpf(i) + mp.mpf(j) / 1024) / 65536)
-        b = edge(mp.mpf(1) / 2 + (mp.mpf(i) + mp.mpf(j + 1) / 1024) / 65536)
-        assert abs(rms(a, b) - z2[t * 1024 + j]) < 1e-6
-    a = edge(mp.mpf(1) / 2 + (mp.mpf(32767) + mp.mpf(1023) / 1024) / 65536)
+    for t, j in ((0, 0), (0, 4096), (1, 8190)):
+        i = 32766 + t
+        a = edge(mp.mpf(1) / 2 + (mp.mpf(i) + mp.mpf(j) / 8192) / 65536)
+        b = edge(mp.mpf(1) / 2 + (mp.mpf(i) + mp.mpf(j + 1) / 8192) / 65536)
+        assert abs(rms(a, b) - z2[t * 8192 + j]) < 1e-6
+    a = edge(mp.mpf(1) / 2 + (mp.mpf(32767) + mp.mpf(8191) / 8192) / 65536)
     assert abs(rms(a, mp.inf) - z2[-1]) < 1e-6
 
 
