@@ -388,50 +388,6 @@ struct TileHdr {
 
 // ---- phase B ---------------------------------------------------------------------------------------------------
 
-// Generic (slow) chunk: the clipped chunks at the two ends of a tile.  Walks the boundary bits sample by sample.
-template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __noinline__ void slow_chunk(const GenParams &p, const float2 *par, const uint8_t *map, const uint8_t *bmap,
-                                        const __half *__restrict__ z16s, const TileHdr h, uint32_t w) {
-    const int s0 = (int)(8 * w) - (int)h.ph;
-    const uint32_t q0 = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);
-    const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
-    const int first = max(s0, 0) - s0;  // first valid slot
-    uint32_t k, nxt = 0;
-    uint32_t bits = 0;
-    if (RAND_DWELL) {
-        k = map[w];
-        bits = bmap[w];
-    } else {
-        k = div_sps(p, (uint32_t)max(s0, 0));
-        nxt = (k + 1) * (uint32_t)p.sps_fixed;
-    }
-    uint4 rw = make_uint4(0, 0, 0, 0);
-    if (NOISY) rw = philox4x32_10_rk(q0 >> 3, h.r_lo, h.r_hi, ST_AMP, p.rk);
-    for (int j = first; j < 8; j++) {
-        const int s = s0 + j;
-        if ((uint32_t)s >= h.S) break;
-        if (RAND_DWELL) {
-            if (j > first && ((bits >> j) & 1u)) k++;
-        } else if ((uint32_t)s >= nxt) {
-            k++;
-            nxt += (uint32_t)p.sps_fixed;
-        }
-        const int e = REV ? 7 - j : j;
-        const float2 ab = par[k];
-        uint32_t v;
-        if (NOISY) {
-            uint32_t x = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
-            if (e & 1) x = __byte_perm(x, x, 0x1032);
-            const uint32_t hw = stratify((x >> 1) & 0xFFFFu, q0 >> 3);
-            const float z = z16(z16s, p.z2, hw, q0 + e, key, ST_AMP_TAIL);
-            v = to_i16_bits(fmaf(z, ab.x, ab.y));
-        } else {
-            v = __float_as_uint(ab.y);
-        }
-        h.out[q0 + e] = (int16_t)v;
-    }
-}
-
 // 32-bit shared addresses of a warp's tile buffer and of the CTA's tables, computed once per kernel
 struct WarpSmem {
     uint32_t par, map, bmap, lut, z;
@@ -448,16 +404,19 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpS
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         const uint32_t wc = wv[c];
-        const uint32_t s0 = 8 * wc - h.ph;  // first tile sample of the chunk
-        q0[c] = REV ? (h.L - h.B - (s0 + 8)) : (h.B + s0);  // emitted position, multiple of 8
+        const int s0 = (int)(8 * wc) - (int)h.ph;  // first tile sample of the chunk; < 0 only for a clipped chunk 0
+        q0[c] = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);  // emitted position, multiple of 8
         uint32_t k0, bm;
         if (RAND_DWELL) {
             k0 = lds_u8(ws.map + wc);
-            bm = lds_u8(ws.bmap + wc) >> 1;
+            bm = lds_u8(ws.bmap + wc);
+            // a clipped chunk 0 starts inside k-mer 0, whose own start bit (at slot ph) is not a boundary to cross
+            if (wc == 0) bm &= ~(1u << h.ph);
+            bm >>= 1;
         } else {
-            k0 = div_sps(p, s0);
+            k0 = div_sps(p, (uint32_t)max(s0, 0));
             bm = 0;
-            for (uint32_t b = (k0 + 1) * (uint32_t)p.sps_fixed - s0; b < 8; b += (uint32_t)p.sps_fixed) bm |= 1u << (b - 1);
+            for (int b = (int)((k0 + 1) * (uint32_t)p.sps_fixed) - s0; b < 8; b += p.sps_fixed) bm |= 1u << (b - 1);
         }
         const uint4 lu = lds_u4(ws.lut + (bm * LUT_COPIES + (lane & (LUT_COPIES - 1))) * 16);
         const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
@@ -518,32 +477,36 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpS
         // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
         const uint4 pk = make_uint4(__byte_perm(v[c][0], v[c][1], 0x5410), __byte_perm(v[c][2], v[c][3], 0x5410),
                                     __byte_perm(v[c][4], v[c][5], 0x5410), __byte_perm(v[c][6], v[c][7], 0x5410));
-        if (st[c]) __stcs(reinterpret_cast<uint4 *>(h.out + q0[c]), pk);
+        if (st[c]) {
+            const int s0 = (int)(8 * wv[c]) - (int)h.ph;
+            if (s0 >= 0 && (uint32_t)(s0 + 8) <= h.S) {
+                __stcs(reinterpret_cast<uint4 *>(h.out + q0[c]), pk);
+            } else {
+                // clipped chunk at an end of the tile (at most two per tile): store only the tile's own samples; the
+                // neighbouring tile computes the same Philox block and stores the rest
+                const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int e = REV ? 7 - j : j;
+                    if (s0 + j >= 0 && (uint32_t)(s0 + j) < h.S) h.out[q0[c] + e] = (int16_t)((pw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                }
+            }
+        }
     }
 }
 
 template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __forceinline__ void emit_tile(const GenParams &p, const WarpSmem &ws, const float2 *par, const uint8_t *map,
-                                          const uint8_t *bmap, const __half *z16s, const TileHdr h, int lane) {
-    const uint32_t nW = (h.S + h.ph + 7) >> 3;
-    // chunks [wlo, whi) lie fully inside the tile; chunk 0 is clipped iff ph > 0, the last one iff it overhangs S
-    const uint32_t wlo = h.ph ? 1u : 0u;
-    const uint32_t whi = (h.S + h.ph) >> 3;
-    for (uint32_t w = wlo + lane; w < whi; w += 32 * NCHUNK) {
+__device__ __forceinline__ void emit_tile(const GenParams &p, const WarpSmem &ws, const TileHdr h, int lane) {
+    const uint32_t nW = (h.S + h.ph + 7) >> 3;  // chunks touched by the tile (the first and last may be clipped)
+    for (uint32_t w = lane; w < nW; w += 32 * NCHUNK) {
         uint32_t wv[NCHUNK];
         bool st[NCHUNK];
 #pragma unroll
         for (int c = 0; c < NCHUNK; c++) {
-            st[c] = w + 32u * c < whi;
+            st[c] = w + 32u * c < nW;
             wv[c] = st[c] ? w + 32u * c : w;  // a missing partner is computed redundantly and not stored
         }
         emit_chunks_fast<NOISY, RAND_DWELL, REV, NCHUNK>(p, ws, h, lane, wv, st);
-    }
-    // the (at most two) clipped chunks at the ends of the tile: generic path, both in one warp-level call
-    if (lane < 2) {
-        const uint32_t w = lane == 0 ? 0u : nW - 1;
-        const bool clipped = lane == 0 ? (wlo == 1u) : (whi < nW && !(nW == 1 && wlo == 1u));
-        if (clipped) slow_chunk<NOISY, RAND_DWELL, REV>(p, par, map, bmap, z16s, h, w);
     }
 }
 
@@ -794,7 +757,7 @@ __global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_
         const TileDesc td = td_next;
         td_next = load_tile_desc(p.tiles, min(tile + stride, p.n_tiles - 1));  // in flight during this tile
         const TileHdr h = prepare_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, td, lane, par, map, bmap, dig, code, model, z16s);
-        emit_tile<NOISY, RAND_DWELL, REV>(p, ws, par, map, bmap, z16s, h, lane);
+        emit_tile<NOISY, RAND_DWELL, REV>(p, ws, h, lane);
         __syncwarp();  // the tile buffer is rewritten by the next prepare_tile
     }
 }
