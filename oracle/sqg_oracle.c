@@ -392,10 +392,10 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                 raw[n++] = to_i16_d((double)s * p->digitisation / p->range - offset);
             }
         } else {
-            double a = (double)o->sd_eff[r] * scale;
-            double b0 = (double)mean * scale;
-            double b = b0 - offset;
-            const float A = (float)a, B = (float)b;
+            /* Philox mode: single precision, rounded once each (A' by the product, B' by the FMA) */
+            const float scale_f = (float)scale, off_f = (float)offset;
+            const float A = o->sd_eff[r] * scale_f;
+            const float B = fmaf(mean, scale_f, -off_f);
             for (int j = 0; j < sps[i]; j++, n++) {
                 /* Philox draws are addressed by the position in the EMITTED signal (after the RNA
                  * reversal of src/gensig.c:348-354), eight 16-bit draws per block */

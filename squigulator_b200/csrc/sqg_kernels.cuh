@@ -349,6 +349,15 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void atoms_or(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 // ---- mbarrier / TMA bulk copy for the one-time table staging (SASS: SYNCS, UBLKCP) ----
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
@@ -390,7 +399,7 @@ struct TileHdr {
 
 // 32-bit shared addresses of a warp's tile buffer and of the CTA's tables, computed once per kernel
 struct WarpSmem {
-    uint32_t par, map, bmap, lut, z;
+    uint32_t par, map, bmap, dig, lut, z;
 };
 
 // NCH chunks of the same lane (w, w+32, ...) in one straight-line block so that their Philox chains and table
@@ -409,10 +418,7 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpS
         uint32_t k0, bm;
         if (RAND_DWELL) {
             k0 = lds_u8(ws.map + wc);
-            bm = lds_u8(ws.bmap + wc);
-            // a clipped chunk 0 starts inside k-mer 0, whose own start bit (at slot ph) is not a boundary to cross
-            if (wc == 0) bm &= ~(1u << h.ph);
-            bm >>= 1;
+            bm = lds_u8(ws.bmap + wc) >> 1;  // (k-mer 0's own start is never marked: it is not a boundary to cross)
         } else {
             k0 = div_sps(p, (uint32_t)max(s0, 0));
             bm = 0;
@@ -432,7 +438,7 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpS
         float zmax = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-            const uint32_t bank4 = ((q0[c] >> 3) & 31u) << 2;  // stratify(): the chunk's Philox block picks the bank
+            const uint32_t bank4 = (q0[c] >> 1) & 0x7Cu;  // stratify(): (block & 31) << 2, the chunk's Philox block picks the bank
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
@@ -448,7 +454,7 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpS
             const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
-                const uint32_t bank4 = ((q0[c] >> 3) & 31u) << 2;
+                const uint32_t bank4 = (q0[c] >> 1) & 0x7Cu;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int e = REV ? 7 - j : j;
@@ -488,7 +494,8 @@ __device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpS
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int e = REV ? 7 - j : j;
-                    if (s0 + j >= 0 && (uint32_t)(s0 + j) < h.S) h.out[q0[c] + e] = (int16_t)((pw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                    // (uint32_t)(s0 + j) < S also rejects the negative positions of a clipped first chunk
+                    if ((uint32_t)(s0 + j) < h.S) h.out[q0[c] + e] = (int16_t)((e & 1) ? (pw[e >> 1] >> 16) : pw[e >> 1]);
                 }
             }
         }
@@ -529,19 +536,23 @@ constexpr int WIN_LOADS = (TK + 8 + 31) / 32;  // byte loads per lane for a tile
 // Source order = latency order: global loads first (base window, per-read values), then the dwell draws (shared
 // memory only) while they fly, then digits -> ranks -> model gathers, then the map/bitmap scatter while the gathers fly.
 template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
-__device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDesc td, int lane, float2 *par, uint8_t *map,
-                                                uint8_t *bmap, uint8_t *dig, const uint8_t *code,
-                                                const float2 *__restrict__ model, const __half *z16s) {
+__device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDesc td, int lane, const WarpSmem &ws,
+                                                const uint8_t *dig, const uint8_t *code, const float2 *__restrict__ model) {
     const int nk_tile = td.nk;
     // (1) the tile's base window: coalesced byte loads, all in flight at once
     uint32_t raw[WIN_LOADS];
     const int nb = nk_tile + p.k - 1;
     const uint8_t *pa_lane = p.bases + td.a_off + lane, *pb_lane = p.bases + td.b_off + lane;
+    if (td.a_rem >= nb || td.a_rem <= 0) {  // the whole window lies in one piece (always, except around a prefix junction)
+        const uint8_t *src = td.a_rem > 0 ? pa_lane : pb_lane;
 #pragma unroll
-    for (int u = 0; u < WIN_LOADS; u++) {
-        const int i = lane + 32 * u;
-        raw[u] = 0;
-        if (i < nb) raw[u] = __ldg((i < td.a_rem ? pa_lane : pb_lane) + 32 * u);
+        for (int u = 0; u < WIN_LOADS; u++) raw[u] = (lane + 32 * u < nb) ? __ldg(src + 32 * u) : 0u;
+    } else {
+#pragma unroll
+        for (int u = 0; u < WIN_LOADS; u++) {
+            const int i = lane + 32 * u;
+            raw[u] = (i < nb) ? __ldg((i < td.a_rem ? pa_lane : pb_lane) + 32 * u) : 0u;
+        }
     }
     // (2) per-read values
     const uint32_t L = __ldg(p.read_siglen + td.read);
@@ -559,7 +570,7 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
     if (RAND_DWELL) {
         const uint32_t blk = (td.kidx0 >> 3) + lane;
         const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
-        const uint32_t zbase = smem_u32(z16s);
+        const uint32_t zbase = ws.z;
         float zmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -575,12 +586,14 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
                     d[j] = dwell_from_z(z16_tail(p.z2, hw, blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
             }
         }
+        if (nk_tile < TK) {  // only the last tile of a segment has lanes beyond its end
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (m0 + j >= nk_tile) d[j] = 0;
+        }
         uint32_t local = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (m0 + j >= nk_tile) d[j] = 0;
-            local += (uint32_t)d[j];
-        }
+        for (int j = 0; j < 8; j++) local += (uint32_t)d[j];
         uint32_t inc = local;
 #pragma unroll
         for (int sh = 1; sh < 32; sh <<= 1) {
@@ -599,7 +612,7 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
     for (int u = 0; u < WIN_LOADS; u++) {
         const int i = lane + 32 * u;
         const uint32_t c = code[raw[u] & 0xFFu];
-        if (i < nb) dig[i] = (uint8_t)(METH ? (c >> 4) : (c & 3u));
+        if (i < nb) sts_u8(ws.dig + i, METH ? (c >> 4) : (c & 3u));
     }
     __syncwarp();
 
@@ -632,9 +645,11 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
                 ranks[j] = rank;
             }
         }
+        if (nk_tile < TK) {
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (m0 + ((j + rot) & 7) >= nk_tile) ranks[j] = 0;
+            for (int j = 0; j < 8; j++)
+                if (m0 + ((j + rot) & 7) >= nk_tile) ranks[j] = 0;
+        }
     }
     float2 mv[8];
 #pragma unroll
@@ -645,24 +660,25 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
         static_assert(MAPC / 16 <= 96, "three 16-byte stores per lane must cover the boundary bitmap");
 #pragma unroll
         for (int u = 0; u < 3; u++)
-            if (lane + 32 * u < MAPC / 16) reinterpret_cast<uint4 *>(bmap)[lane + 32 * u] = make_uint4(0, 0, 0, 0);
+            if (lane + 32 * u < MAPC / 16) sts_zero16(ws.bmap + 16 * (lane + 32 * u));
         __syncwarp();
         if (active) {
-            uint32_t oo = o;
+            uint32_t pos = o + ph;  // the k-mer starts at bit (pos&7) of chunk (pos>>3)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int m = m0 + j;
-                if (m < nk_tile) {
+                if (nk_tile == TK || m < nk_tile) {
                     // chunks whose first (clipped) sample falls inside this k-mer get it as their first k-mer
-                    const uint32_t pos = oo + ph;  // the k-mer starts at bit (pos&7) of chunk (pos>>3)
-                    uint32_t w0 = m == 0 ? 0u : (pos + 7) >> 3;
-                    const uint32_t w1 = (pos + (uint32_t)d[j] + 7) >> 3;
-                    if (w0 < w1) map[w0] = (uint8_t)m;
-                    if (w0 + 1 < w1) map[w0 + 1] = (uint8_t)m;
-                    if (w0 + 2 < w1) map[w0 + 2] = (uint8_t)m;
-                    for (w0 += 3; w0 < w1; w0++) map[w0] = (uint8_t)m;
-                    atomicOr(reinterpret_cast<uint32_t *>(bmap) + (pos >> 5), 1u << (pos & 31));
-                    oo += (uint32_t)d[j];
+                    uint32_t w0 = (j == 0 && m0 == 0) ? 0u : (pos + 7) >> 3;
+                    const uint32_t end = pos + (uint32_t)d[j];
+                    const uint32_t w1 = (end + 7) >> 3;
+                    const uint32_t a = ws.map + w0;
+                    if (w0 < w1) sts_u8(a, (uint32_t)m);
+                    if (w0 + 1 < w1) sts_u8(a + 1, (uint32_t)m);
+                    if (w0 + 2 < w1) sts_u8(a + 2, (uint32_t)m);
+                    for (w0 += 3; w0 < w1; w0++) sts_u8(ws.map + w0, (uint32_t)m);
+                    if (!(j == 0 && m0 == 0)) atoms_or(ws.bmap + ((pos >> 3) & ~3u), 1u << (pos & 31));
+                    pos = end;
                 }
             }
         }
@@ -675,20 +691,19 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
 
     // (7) per-k-mer parameters from the gathered (level_mean, level_stdv)
     if (active) {
+        const float scale_f = (float)p.scale, off_f = (float)offset;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             float2 pr;
             if (NOISY) {
-                const float sd = __fmul_rn(mv[j].y, p.amp_noise);  // float product, src/sim.c:249
-                const double a = __dmul_rn((double)sd, p.scale);
-                const double b = __dsub_rn(__dmul_rn((double)mv[j].x, p.scale), offset);
-                pr = make_float2((float)a, (float)b);
+                // single precision, rounded once each: A' = (stdv*amp_noise)*scale, B' = fma(mean, scale, -offset)
+                pr = make_float2(__fmul_rn(__fmul_rn(mv[j].y, p.amp_noise), scale_f), fmaf(mv[j].x, scale_f, -off_f));
             } else {
                 // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
                 const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
                 pr = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
             }
-            par[m0 + ((j + rot) & 7)] = pr;  // rows beyond the tile are never read
+            sts_f2(ws.par + 8 * (m0 + ((j + rot) & 7)), pr);  // rows beyond the tile are never read
         }
     }
     __syncwarp();
@@ -746,7 +761,7 @@ __global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_
     uint8_t *dig = smem + lay.digit + warp * DIG_BYTES;
     if (smem_u32(par) + TK * 8 + 64 >= 0x10000u) __trap();
     const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
-    const WarpSmem ws{smem_u32(par), smem_u32(map), smem_u32(bmap), smem_u32(lut), smem_u32(z16s)};
+    const WarpSmem ws{smem_u32(par), smem_u32(map), smem_u32(bmap), smem_u32(dig), smem_u32(lut), smem_u32(z16s)};
 
     // ---- main loop: this warp's tiles ----
     const int gwarp = blockIdx.x * nw + warp;
@@ -756,7 +771,7 @@ __global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_
     for (int tile = gwarp; tile < p.n_tiles; tile += stride) {
         const TileDesc td = td_next;
         td_next = load_tile_desc(p.tiles, min(tile + stride, p.n_tiles - 1));  // in flight during this tile
-        const TileHdr h = prepare_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, td, lane, par, map, bmap, dig, code, model, z16s);
+        const TileHdr h = prepare_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, td, lane, ws, dig, code, model);
         emit_tile<NOISY, RAND_DWELL, REV>(p, ws, h, lane);
         __syncwarp();  // the tile buffer is rewritten by the next prepare_tile
     }
