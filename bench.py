@@ -377,7 +377,7 @@ def main():
                            "reads_per_step_per_gpu": res["reads_per_step_per_gpu"],
                            "samples_per_step_per_gpu": res["samples_per_step_per_gpu"],
                            "l2": "output per step (GBs) far exceeds the 126 MB L2; no flush needed",
-                           "rng": "philox4x32-10", "parallelism": f"reads sharded over {world} GPU(s), no hot-path collective"},
+                           "rng": "philox4x32-7", "parallelism": f"reads sharded over {world} GPU(s), no hot-path collective"},
                 "clocks": res["clocks"], "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "cpu_baseline": cpu, "store_only_gbs": res["store_only_gbs"],
                 "wall_s_timed_region": res["wall_s"], "other_workloads": extra}

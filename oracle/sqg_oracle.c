@@ -76,12 +76,15 @@ double sqo_lehmer_normal(int64_t *state, double m, double s) {
     return x * s + m;
 }
 
-/* ------------------------------------------------------------------ Philox4x32-10 */
+/* ------------------------------------------------------------------ Philox4x32-R */
 
-void sqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* Salmon, Moraes, Dror, Shaw 2011.  `rounds` = 10 is the standard generator (Random123 known answers);
+ * the signal path uses SQO_PHILOX_ROUNDS = 7, the smallest round count the authors report as
+ * Crush-resistant, as the product does (squigulator_b200/csrc/sqg_device.cuh: PHILOX_ROUNDS). */
+void sqo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -95,66 +98,52 @@ void sqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+void sqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    sqo_philox4x32(ctr, key, 10, out);
+}
+
+#define SQO_PHILOX_ROUNDS 7
+static void philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    sqo_philox4x32(ctr, key, SQO_PHILOX_ROUNDS, out);
+}
+
 /* counter word 3 = stream tag */
 enum { ST_AMP = 0, ST_DWELL = 1, ST_READ = 2, ST_AMP_TAIL = 3, ST_DWELL_TAIL = 4, ST_READ_TAIL = 5 };
 
-#define Z16_N 65536
-#define Z_TAIL_FIRST 32766
+#define Z32_N 32768
+#define Z_TAIL_IDX 0x3FE0u /* (m = 511) << 5 | (class 0): the outermost half-normal cell */
 #define Z2_SUB 8192
 
-/* IEEE binary16 -> binary32, exact */
-static float half_to_float(uint16_t h) {
-    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu, bits;
-    if (e == 0) {
-        if (m == 0) {
-            bits = sign;
-        } else { /* subnormal: normalise */
-            int sh = 0;
-            while (!(m & 0x400u)) { m <<= 1; sh++; }
-            bits = sign | ((uint32_t)(113 - sh) << 23) | ((m & 0x3FFu) << 13);
-        }
-    } else if (e == 31) {
-        bits = sign | 0x7F800000u | (m << 13);
-    } else {
-        bits = sign | ((e + 112) << 23) | (m << 13);
-    }
-    float f;
-    memcpy(&f, &bits, 4);
-    return f;
-}
-
-/* 16-bit uniform -> N(0,1) by quantile table (bit 15 = sign, bits 0-14 = half-normal cell); the 2
- * outermost cells take 13 more bits from a dedicated Philox block addressed by (c0,c1,c2,tail_stream).
- * zt = the bytes of squigulator_b200/data/ztable_v2.bin: Z16[65536] binary16, then Z2[16384] binary32.
- * DESIGN.md "z16". */
-float sqo_z16(const void *zt, uint32_t h, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
+/* Table normal (DESIGN.md "Z32").  idx = (r << 5) | c: r = ten random bits (bit 9 = sign, bits 0-8 = slot m),
+ * c = the CLASS = low five bits of the draw's Philox block number.  The entry is a 4-byte float whose word
+ * index has c in its low five bits = the shared-memory bank, so the 32 lanes of a warp (32 consecutive
+ * blocks) never collide; a class owns 512 half-normal cells spread evenly over the quantile range and is
+ * scaled to unit variance (scripts/make_ztable.py).  The outermost cell (class 0, m = 511) takes 13 more
+ * bits from a dedicated Philox block addressed by (c0,c1,c2,tail_stream).
+ * zt = the bytes of squigulator_b200/data/ztable_v3.bin: Z32[32768] binary32, then Z2[8192] binary32. */
+float sqo_z32(const void *zt, uint32_t idx, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
               uint32_t tail_stream) {
-    const uint16_t *z16 = (const uint16_t *)zt;
-    const float *z2 = (const float *)((const unsigned char *)zt + Z16_N * 2);
-    uint32_t i = h & 0x7FFFu;
-    if (i >= Z_TAIL_FIRST) {
+    const float *z32 = (const float *)zt;
+    const float *z2 = z32 + Z32_N;
+    idx &= Z32_N - 1;
+    if ((idx & 0x3FFFu) == Z_TAIL_IDX) {
         uint32_t ctr[4] = {c0, c1, c2, tail_stream}, w[4];
-        sqo_philox4x32_10(ctr, key, w);
-        float z = z2[(i - Z_TAIL_FIRST) * Z2_SUB + (w[0] & (Z2_SUB - 1))];
-        return (h & 0x8000u) ? -z : z;
+        philox(ctr, key, w);
+        float z = z2[w[0] & (Z2_SUB - 1)];
+        return (idx & 0x4000u) ? -z : z;
     }
-    return half_to_float(z16[h & 0xFFFFu]);
+    return z32[idx];
 }
 
-/* Bank-stratified table index (DESIGN.md "z16"): bits 1-5 of the 16-bit draw are replaced by the low five
- * bits of the draw's Philox block number.  Those bits select the shared-memory bank of the 2-byte table entry,
- * so the 32 lanes of a warp (which handle 32 consecutive blocks) never collide; a draw still picks uniformly
- * among 2^11 cells spread evenly over the whole table, and every table cell is used by some block residue. */
-static uint32_t stratify(uint32_t h, uint32_t block) { return (h & 0xFFC1u) | ((block & 31u) << 1); }
-
-/* the j-th 16-bit draw (j in 0..7) of a Philox block: even draws are bits 1..16 of word j/2, odd draws bits 1..16
- * of the same word rotated by 16 (i.e. bits 17..31 and 0).  The two draws of a word share no bit that survives
- * stratify(), and on the GPU `word & 0x1FF82` is directly the byte offset of the table entry. */
-static uint32_t halfword(const uint32_t w[4], uint32_t j) {
+/* the j-th 10-bit draw (j in 0..7) of a Philox block: even draws are bits 7..16 of word j/2, odd draws bits
+ * 7..16 of the same word rotated by 16 (i.e. bits 23..31 and 0).  On the GPU `word & 0x1FF80` is directly
+ * the byte offset of the class-0 table entry. */
+static uint32_t draw10(const uint32_t w[4], uint32_t j) {
     uint32_t x = w[j >> 1];
     if (j & 1) x = (x >> 16) | (x << 16);
-    return (x >> 1) & 0xFFFFu;
+    return (x >> 7) & 0x3FFu;
 }
+static uint32_t zindex(const uint32_t w[4], uint32_t j, uint32_t block) { return (draw10(w, j) << 5) | (block & 31u); }
 
 /* ------------------------------------------------------------------ handle */
 
@@ -251,6 +240,30 @@ static int16_t to_i16_f(float v) {
     return (int16_t)(uint16_t)((uint32_t)i & 0xFFFFu);
 }
 
+/* single-precision fused multiply-add rounded toward zero (PTX fma.rz.f32).  The exact value of x*y + z is
+ * formed in double with round-to-odd (x*y is exact in double; the addition is done toward zero and made
+ * sticky), then rounded toward zero to float: 53 bits with a sticky last bit round correctly to 24. */
+#include <fenv.h>
+static float fma_rz(float x, float y, float z);
+float sqo_fma_rz(float x, float y, float z) { return fma_rz(x, y, z); }
+static float fma_rz(float x, float y, float z) {
+    const int mode = fegetround();
+    fesetround(FE_TOWARDZERO);
+    volatile double p = (double)x * (double)y; /* exact: 24 x 24 bits */
+    volatile double zz = (double)z;
+    feclearexcept(FE_INEXACT);
+    volatile double s = p + zz;                /* toward zero */
+    if (fetestexcept(FE_INEXACT)) {            /* sticky bit: round to odd */
+        union { double d; uint64_t u; } c;
+        c.d = s;
+        c.u |= 1u;
+        s = c.d;
+    }
+    volatile float r = (float)s;               /* toward zero again */
+    fesetround(mode);
+    return r;
+}
+
 int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index, int tid, double *offset_out,
                     double *median_out, int16_t **sig_out, int32_t **ss_out, int64_t *ss_n_out) {
     oracle_t *o = (oracle_t *)hv;
@@ -276,18 +289,22 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
         offset = sqo_lehmer_normal(&ls->offset, p->offset_mean, p->offset_std);
         median = sqo_lehmer_normal(&ls->median, p->median_before_mean, p->median_before_std);
     } else {
-        /* one Philox block per read; each deviate mixes two table normals cos(35deg)*z1 +
-         * sin(35deg)*z2 so that per-read values have ~2^30 atoms (unit variance; an irrational-looking ratio keeps
-         * sums of the binary16 table values from colliding) */
+        /* one Philox block per read: draws 0-3 make the offset deviate, draws 4-7 the median_before deviate, each
+         * a unit-norm mix of four table normals (weights cos/sin products of 35, 40, 55 degrees) so that per-read
+         * values have ~2^40 atoms; the draws' classes walk with the read index so that reads use all 32 */
+        static const double W4[4] = {0.6275068715971331, 0.43938504177070503, 0.3686878264946124, 0.5265407845183632};
         uint32_t ctr[4] = {0, r_lo, r_hi, ST_READ}, w[4];
-        sqo_philox4x32_10(ctr, o->key, w);
+        philox(ctr, o->key, w);
         double z[2];
         for (int d = 0; d < 2; d++) {
-            float za = sqo_z16(o->zt, w[d] & 0xFFFFu, o->key, 2 * d, r_lo, r_hi, ST_READ_TAIL);
-            float zb = sqo_z16(o->zt, w[d] >> 16, o->key, 2 * d + 1, r_lo, r_hi, ST_READ_TAIL);
-            double a = (double)za * 0.8191520442889918;
-            double b = (double)zb * 0.573576436351046;
-            z[d] = a + b;
+            double t[4];
+            for (uint32_t u = 0; u < 4; u++) {
+                uint32_t j = 4 * (uint32_t)d + u;
+                float zz = sqo_z32(o->zt, zindex(w, j, 8 * r_lo + j), o->key, j, r_lo, r_hi, ST_READ_TAIL);
+                t[u] = (double)zz * W4[u];
+            }
+            double ab = t[0] + t[1], cd = t[2] + t[3];
+            z[d] = ab + cd;
         }
         double t0 = z[0] * p->offset_std;
         offset = t0 + p->offset_mean;
@@ -360,9 +377,9 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                  * the next multiple of 8 so that every block of 8 draws lies inside one segment */
                 int64_t di = i < nk_seg[0] ? i : ((nk_seg[0] + 7) & ~(int64_t)7) + (i - nk_seg[0]);
                 uint32_t ctr[4] = {(uint32_t)(di >> 3), r_lo, r_hi, ST_DWELL}, w[4];
-                sqo_philox4x32_10(ctr, o->key, w);
-                float z = sqo_z16(o->zt, stratify(halfword(w, (uint32_t)(di & 7)), (uint32_t)(di >> 3)), o->key,
-                                  (uint32_t)di, r_lo, r_hi, ST_DWELL_TAIL);
+                philox(ctr, o->key, w);
+                float z = sqo_z32(o->zt, zindex(w, (uint32_t)(di & 7), (uint32_t)(di >> 3)), o->key, (uint32_t)di, r_lo,
+                                  r_hi, ST_DWELL_TAIL);
                 /* Philox mode: single-precision FMA, round to nearest (ties to even; the reference's
                  * round() differs only on exact .5 ties, which table normals do not produce) */
                 d = (int)lrintf(fmaf(z, (float)p->dwell_std, (float)p->dwell_mean));
@@ -392,18 +409,25 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                 raw[n++] = to_i16_d((double)s * p->digitisation / p->range - offset);
             }
         } else {
-            /* Philox mode: single precision, rounded once each (A' by the product, B' by the FMA) */
+            /* Philox mode: single precision.  A' is rounded once by the product, B' once by the FMA, then B' is put
+             * on the 2^-8 grid: Bq = (B' + 32768) - 32768 in float arithmetic (for every sane profile B' + 32768
+             * lies in [32768, 65536), where floats are spaced 2^-8 apart).  The sample is the single-precision FMA
+             * z*A' + Bq ROUNDED TOWARD ZERO, truncated toward zero like the reference's store (src/gensig.c:270) and
+             * wrapped to 16 bits.  The GPU gets the same integer for 0 <= value < 32768 from the mantissa of
+             * fma.rz(z, A', Bq + 32768) without a conversion, and falls back to this very expression otherwise. */
             const float scale_f = (float)scale, off_f = (float)offset;
             const float A = o->sd_eff[r] * scale_f;
             const float B = fmaf(mean, scale_f, -off_f);
+            volatile float Bm = B + 32768.0f;
+            const float Bq = Bm - 32768.0f;
             for (int j = 0; j < sps[i]; j++, n++) {
                 /* Philox draws are addressed by the position in the EMITTED signal (after the RNA
-                 * reversal of src/gensig.c:348-354), eight 16-bit draws per block */
+                 * reversal of src/gensig.c:348-354), eight 10-bit draws per block */
                 uint32_t q = (uint32_t)(rna ? total - 1 - n : n);
                 uint32_t ctr[4] = {q >> 3, r_lo, r_hi, ST_AMP}, w[4];
-                sqo_philox4x32_10(ctr, o->key, w);
-                float z = sqo_z16(o->zt, stratify(halfword(w, q & 7), q >> 3), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
-                raw[n] = to_i16_f(fmaf(z, A, B));
+                philox(ctr, o->key, w);
+                float z = sqo_z32(o->zt, zindex(w, q & 7, q >> 3), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
+                raw[n] = to_i16_f(fma_rz(z, A, Bq));
             }
         }
     }

@@ -52,7 +52,7 @@ typedef struct {
 } sqo_config_t;
 
 /* model: num_kmer interleaved (level_mean, level_stdv) floats == model_t[] (src/sq.h:61-68).
- * ztable: the bytes of squigulator_b200/data/ztable_v2.bin (Z16[65536] binary16 ++ Z2[16384] binary32);
+ * ztable: the bytes of squigulator_b200/data/ztable_v3.bin (Z32[32768] binary32 ++ Z2[8192] binary32);
  * NULL allowed in legacy mode. */
 void *sqo_open(const sqo_config_t *cfg, const float *model, const void *ztable);
 void sqo_close(void *h);
@@ -71,8 +71,10 @@ uint32_t sqo_kmer_rank(const char *s, uint32_t k);      /* src/seq.h:31-42 */
 uint32_t sqo_meth_kmer_rank(const char *s, uint32_t k); /* src/seq.h:62-74 */
 double sqo_lehmer_next(int64_t *state);                 /* src/rand.h:79-85 */
 double sqo_lehmer_normal(int64_t *state, double m, double s); /* src/rand.h:87-94 */
-float sqo_z16(const void *ztable, uint32_t h, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
+void sqo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
+float sqo_z32(const void *ztable, uint32_t idx, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
               uint32_t tail_stream);
+float sqo_fma_rz(float x, float y, float z);            /* PTX fma.rz.f32, restated */
 
 #ifdef __cplusplus
 }

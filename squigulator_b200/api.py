@@ -92,7 +92,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsqg.so")
+    # SQG_LIB: a differently tuned build of the same library (kernel experiments, scripts/perf_matrix.py)
+    return os.environ.get("SQG_LIB") or os.path.join(_HERE, "libsqg.so")
 
 
 def load_library():

@@ -28,7 +28,7 @@
 #include "sqg_kernels.cuh"
 #include "sqg_legacy.cuh"
 
-extern "C" const unsigned char sqg_ztable_blob[];  // Z16 (binary16) ++ Z2 (binary32), embedded from data/ztable_v2.bin (ztable_blob.S)
+extern "C" const unsigned char sqg_ztable_blob[];  // Z32 ++ Z2 (binary32), embedded from data/ztable_v3.bin (ztable_blob.S)
 
 namespace {
 
@@ -104,6 +104,7 @@ struct Slot {
     DevBuf<ReadDesc> d_reads;
     DevBuf<TileDesc> d_tiles;
     DevBuf<uint32_t> d_tile_sum, d_siglen, d_n0;
+    DevBuf<uint4> d_dwells;  // TK uint16 per tile (K1 -> K4)
     DevBuf<int64_t> d_sigoff, d_meta;
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
@@ -125,7 +126,7 @@ struct Slot {
     int64_t arena_need = 0, total_samples = 0;
     bool const_written = false;
     void release() {
-        d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release();
+        d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release(); d_dwells.release();
         d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
         d_offset.release(); d_median.release(); d_sig.release(); d_ss.release();
         d_rank.release(); d_rank_sorted.release(); d_idx.release(); d_idx_sorted.release(); d_dsorted.release();
@@ -166,13 +167,11 @@ struct sqg_ctx {
     int num_sms = 0;
     std::string err;
     DevBuf<float2> d_model;
-    DevBuf<unsigned char> d_z;  // Z16 ++ Z2
+    DevBuf<float4> d_pair_model;  // by (k+1)-mer: the parameters of both of its k-mers (base-4 models)
+    DevBuf<unsigned char> d_z;  // Z32 ++ Z2
     GenParams base;     // configuration-derived part of the kernel parameters
     bool noisy = false, rand_dwell = false, meth = false, rev = false, prefix = false;
-    int model_in_smem = 0;
-    size_t k4_smem = 0;
     int k4_grid_per_sm = 1;
-    int k4_warps = 16;
     // SQG_RNG_LEGACY: positions reached in the reference's streams (src/sim.c:215-258, thread 0)
     bool legacy = false;
     uint64_t leg_dwell_pos = 0, leg_read_pos = 0;
@@ -214,7 +213,7 @@ typedef void (*k4_fn)(const GenParams);
 template <int I>
 struct K4Table {
     static void fill(k4_fn *t) {
-        t[I] = (k4_fn)signal_kernel<(I >> 4) & 1, (I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
+        t[I] = (k4_fn)signal_kernel<(I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
         K4Table<I - 1>::fill(t);
     }
 };
@@ -223,15 +222,15 @@ struct K4Table<-1> {
     static void fill(k4_fn *) {}
 };
 
-// the 32 instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>
-k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev, bool model_smem) {
-    static k4_fn tab[32];
+// the 16 instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV>
+k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev) {
+    static k4_fn tab[16];
     static bool init = false;
     if (!init) {
-        K4Table<31>::fill(tab);
+        K4Table<15>::fill(tab);
         init = true;
     }
-    return tab[(noisy << 4) | (rnd << 3) | (meth << 2) | (rev << 1) | (int)model_smem];
+    return tab[(noisy << 3) | (rnd << 2) | (meth << 1) | (int)rev];
 }
 
 int slot_init(sqg_ctx *ctx, Slot &s) {
@@ -320,8 +319,8 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     s.total_bases = total_bases; s.first_read = first_read; s.want = want;
 
     // device buffers + uploads
-    const bool fresh = s.d_bases.cap < (size_t)(CONST_REGION + total_bases + 16);
-    CU(s.d_bases.ensure((size_t)(CONST_REGION + total_bases + 16), false, s.stream));
+    const bool fresh = s.d_bases.cap < (size_t)(CONST_REGION + total_bases + 64);
+    CU(s.d_bases.ensure((size_t)(CONST_REGION + total_bases + 64), false, s.stream));
     if (fresh || !s.const_written) {
         unsigned char c[CONST_REGION];
         memset(c, 0, sizeof c);
@@ -344,6 +343,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     const size_t nt = (size_t)std::max<int64_t>(ntile, 1), nr = (size_t)std::max<int64_t>(n_reads, 1);
     CU(s.d_tiles.ensure(nt, false, s.stream));
     CU(s.d_tile_sum.ensure(nt, false, s.stream));
+    if (ctx->rand_dwell && !ctx->legacy) CU(s.d_dwells.ensure(nt * (TK / 8), false, s.stream));
     CU(s.d_siglen.ensure(nr, false, s.stream));
     CU(s.d_n0.ensure(nr, false, s.stream));
     CU(s.d_sigoff.ensure(nr, false, s.stream));
@@ -358,7 +358,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
 GenParams slot_params(sqg_ctx *ctx, Slot &s) {
     GenParams p = ctx->base;
     p.bases = s.d_bases.p; p.segs = s.d_segs.p; p.reads = s.d_reads.p;
-    p.tiles = s.d_tiles.p; p.tile_sum = s.d_tile_sum.p;
+    p.tiles = s.d_tiles.p; p.tile_sum = s.d_tile_sum.p; p.dwells = s.d_dwells.p;
     p.read_siglen = s.d_siglen.p; p.read_n0 = s.d_n0.p; p.read_sigoff = s.d_sigoff.p;
     p.read_offset = s.d_offset.p; p.read_median = s.d_median.p; p.meta = s.d_meta.p;
     p.sig = s.d_sig.p; p.ss = s.d_ss.p;
@@ -400,11 +400,15 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
         ctx->launches += 3;
     } else {
         if (ctx->rand_dwell) {
-            dwell_sum_kernel<<<g1, K1_THREADS, 0, s.stream>>>(p);
+            dwell_kernel<<<g1, K1_THREADS, 0, s.stream>>>(p);
             ctx->launches++;
             read_plan_kernel<true><<<g2, 256, 0, s.stream>>>(p);
         } else {
             read_plan_kernel<false><<<g2, 256, 0, s.stream>>>(p);
+            if (p.want_ss && s.total_kmers > 0) {  // aln->ss of the fixed-dwell modes (src/gensig.c:273-281)
+                fixed_ss_kernel<<<(int)((s.total_kmers + 255) / 256), 256, 0, s.stream>>>(p, s.total_kmers);
+                ctx->launches++;
+            }
         }
         ctx->launches++;
     }
@@ -479,11 +483,11 @@ int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent
     if (s.n_reads == 0) return SQG_OK;
     if (ctx->legacy) return slot_generate_legacy(ctx, s);
     const GenParams p = slot_params(ctx, s);
-    const int grid = (int)std::min<int64_t>((s.n_tiles + ctx->k4_warps - 1) / ctx->k4_warps, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
+    const int grid = (int)std::min<int64_t>((s.n_tiles + K4_WARPS - 1) / K4_WARPS, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
     if (before) CU(cudaEventRecord(before, s.stream));
     void *args[] = {(void *)&p};
-    CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(ctx->k4_warps * 32), args, ctx->k4_smem, s.stream));
+    CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(K4_THREADS), args, SM_TOTAL, s.stream));
     if (after) CU(cudaEventRecord(after, s.stream));
     ctx->launches++;
     if (ctx->prefix && ctx->rev) {
@@ -630,7 +634,7 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
         b.T = (int32_t)T;
         b.sps_magic = sps == 1 ? 0u : (uint32_t)(0x100000000ull / sps) + 1u;  // sps == 1 is special-cased in div_sps()
     }
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < PHILOX_ROUNDS; r++) {
         b.rk[2 * r] = b.key0 + (uint32_t)r * 0x9E3779B9u;
         b.rk[2 * r + 1] = b.key1 + (uint32_t)r * 0xBB67AE85u;
     }
@@ -652,7 +656,7 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     CU(ctx->d_model.ensure(n));
     if (h_model) CU(cudaMemcpy(ctx->d_model.p, h_model, n * sizeof(float2), cudaMemcpyHostToDevice));
     else CU(cudaMemcpy(ctx->d_model.p, d_model_in, n * sizeof(float2), cudaMemcpyDeviceToDevice));
-    const size_t zbytes = (size_t)Z16_N * 2 + Z2_N * sizeof(float);
+    const size_t zbytes = (size_t)Z32_BYTES + Z2_SUB * sizeof(float);
     CU(ctx->d_z.ensure(zbytes));
     CU(cudaMemcpy(ctx->d_z.p, sqg_ztable_blob, zbytes, cudaMemcpyHostToDevice));
     if (ctx->legacy) {
@@ -660,28 +664,57 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
         CU(cudaMemset(ctx->d_cnt_kmer.p, 0, n * sizeof(uint64_t)));
     }
     ctx->base.model = ctx->d_model.p;
-    ctx->base.z16 = reinterpret_cast<const __half *>(ctx->d_z.p);
-    ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z16_N * 2);
+    if (!ctx->meth && !ctx->legacy) {
+        // the model again, indexed by (k+1)-mer: one 16-byte gather serves two consecutive k-mers (pair_model_kernel)
+        const uint64_t n_pair = 4ull * n;
+        if (n_pair * sizeof(float4) > (256ull << 20)) return fail(ctx, SQG_ERR_ARG, "k-mer size too large for the paired model table");
+        CU(ctx->d_pair_model.ensure((size_t)n_pair));
+        pair_model_kernel<<<(unsigned)((n_pair + 255) / 256), 256>>>(ctx->d_model.p, ctx->d_pair_model.p, (uint32_t)n_pair, ctx->base.kmask);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        ctx->base.pair_model = ctx->d_pair_model.p;
+    }
+    ctx->base.z32 = reinterpret_cast<const float *>(ctx->d_z.p);
+    ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z32_BYTES);
 
-    // shared-memory plan of the signal kernel: per-warp tile buffers + boundary LUT + quantile table (+ the pore model
-    // when it is small: R9 6-mer = 32 KB, R9 RNA 5-mer = 8 KB).  As many warps as fit, at most K4_MAX_WARPS.
-    const bool use_z = ctx->noisy || ctx->rand_dwell;
-    ctx->model_in_smem = (!ctx->meth && n <= 4096) ? 1 : 0;
-    ctx->base.model_in_smem = ctx->model_in_smem;
-    const uint32_t model_bytes = ctx->model_in_smem ? (uint32_t)(n * sizeof(float2)) : 0;
-    const size_t smem_max = prop.sharedMemPerBlockOptin;
-    int nw = K4_MAX_WARPS;
-    while (nw > 1 && k4_layout(nw, use_z, model_bytes).total > smem_max) nw--;
-    const K4Layout lay = k4_layout(nw, use_z, model_bytes);
-    if (lay.total > smem_max || lay.par + (uint32_t)nw * TK * 8 + 2048 >= 0x10000u)
-        return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
-    ctx->k4_warps = nw;
-    ctx->base.lay = lay;
-    ctx->k4_smem = lay.total;
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->model_in_smem != 0);
-    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    // The sample kernel reads the int16 straight out of the mantissa of fma.rz(z, A', B' + 32768) and relies on bit 23
+    // to flag everything outside [0, 32768); that flag is reliable while 16384 <= z*A' + B' + 32768 < 131072 for every
+    // k-mer, every |z| <= Z_MAX and every offset a read can draw.  Check it once over the model; otherwise (absurd
+    // profiles or models) every sample takes the exact path (GenParams::wide).
+    if (ctx->noisy && !ctx->legacy) {
+        std::vector<float2> hm(n);
+        CU(cudaMemcpy(hm.data(), ctx->d_model.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+        const sqg_profile_t &pr = ctx->cfg.profile;
+        const double scale = pr.digitisation / pr.range;
+        const double off_span = 12.0 * std::fabs(pr.offset_std);  // |deviate| <= (sum of the four weights) * Z_MAX = 11.6
+        const bool ideal = (ctx->cfg.flags & SQG_IDEAL) != 0;
+        const double off_lo = pr.offset_mean - (ideal ? 0.0 : off_span), off_hi = pr.offset_mean + (ideal ? 0.0 : off_span);
+        double lo = 1e300, hi = -1e300;
+        bool finite = std::isfinite(scale) && std::isfinite(off_lo) && std::isfinite(off_hi) && std::isfinite((double)ctx->cfg.amp_noise);
+        for (size_t i = 0; i < n && finite; i++) {
+            const double a = std::fabs((double)hm[i].y * (double)ctx->cfg.amp_noise * scale) * ((double)Z_MAX + 0.01) + 2.0;
+            const double m = (double)hm[i].x * scale;
+            if (!std::isfinite(a) || !std::isfinite(m)) { finite = false; break; }
+            lo = std::min(lo, m - off_hi - a);
+            hi = std::max(hi, m - off_lo + a);
+        }
+        ctx->base.wide = (finite && lo > -16000.0 && hi < 98000.0) ? 0 : 1;
+    }
+
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    if (SM_TOTAL > prop.sharedMemPerBlockOptin) return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
+    {
+        // the sample loop addresses shared memory absolutely: dynamic array = reserved kilobyte + no static shared memory
+        int reserved = 0;
+        cudaFuncAttributes fa;
+        CU(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device));
+        CU(cudaFuncGetAttributes(&fa, (const void *)fn));
+        if ((uint32_t)reserved + (uint32_t)fa.sharedSizeBytes != SMEM_ORIGIN)
+            return fail(ctx, SQG_ERR_CUDA, "signal kernel: unexpected origin of dynamic shared memory");
+    }
+    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, nw * 32, lay.total));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, K4_THREADS, SM_TOTAL));
     if (occ < 1) return fail(ctx, SQG_ERR_CUDA, "signal kernel does not fit on an SM");
     ctx->k4_grid_per_sm = occ;
 

@@ -36,8 +36,8 @@ struct ReadDesc {
     int32_t pad;
 };
 
-// Everything the dwell pass and the signal kernel need to know about a tile, in one 48-byte record
-// (written by K0, completed by K2) so that a producer warp reaches its bases with a single dependent load.
+// Everything the dwell pass and the signal kernel need to know about a tile, in one 80-byte record (written by K0,
+// completed by K2) so that a warp reaches its bases, its dwells and its place in the output with independent loads.
 struct __align__(16) TileDesc {
     int64_t a_off;   // window byte i < a_rem is bases[a_off + i]   (piece a of the segment)
     int64_t b_off;   // window byte i >= a_rem is bases[b_off + i]  (piece b)
@@ -46,15 +46,15 @@ struct __align__(16) TileDesc {
     int32_t read;    // local read index
     uint32_t kidx0;  // dwell draw index of the tile's first k-mer (multiple of 8)
     int64_t ss_pos;  // where the tile's dwells go in ss[]
-    uint32_t B;      // first logical sample of the tile within the read (filled by K2)
+    uint32_t B;      // first logical sample of the tile within the read (K2)
+    uint32_t S;      // samples in the tile (K2)
+    double offset;   // the read's ADC offset (K2)
+    uint32_t L;      // samples in the read (K2)
     uint32_t pad;
+    uint32_t r_lo, r_hi;  // global read index = Philox counter words 1, 2 (K0)
+    uint32_t pad2[2];
 };
-
-// Shared-memory layout of the signal kernel (byte offsets into dynamic shared memory; computed on the host by
-// k4_layout() and passed in the kernel parameters, i.e. the constant bank)
-struct K4Layout {
-    uint32_t par, map, bmap, digit, lut, code, mbar, z16, model, total;
-};
+static_assert(sizeof(TileDesc) == 80, "TileDesc is loaded as five 16-byte words");
 
 struct GenParams {
     // inputs
@@ -62,11 +62,13 @@ struct GenParams {
     const SegDesc *segs;
     const ReadDesc *reads;
     const float2 *model;  // (level_mean, level_stdv) by rank
-    const __half *z16;    // Z16[65536]
-    const float *z2;      // Z2[2*8192]
+    const float4 *pair_model;  // by (k+1)-mer rank: the parameters of its two k-mers (first k bases, last k bases); base-4 models only
+    const float *z32;     // Z32[32768]
+    const float *z2;      // Z2[8192]
     // plan (written by K0-K3, read by K4)
     TileDesc *tiles;
     uint32_t *tile_sum;
+    uint4 *dwells;        // per tile: TK dwells as uint16 (32 x uint4), written by K1 (random-dwell modes)
     uint32_t *read_siglen;
     uint32_t *read_n0;
     int64_t *read_sigoff;
@@ -82,7 +84,7 @@ struct GenParams {
     int32_t k;         // k-mer size
     uint32_t kmask;    // base 4: 4^k-1;  base 5: 5^(k-1)
     uint32_t num_kmer;
-    int32_t model_in_smem;
+    int32_t wide;      // 1: the model/profile does not guarantee 16384 <= sample + 32768 < 131072 -> exact path for every sample
     // profile (src/sq.h:47-58) and options
     double digitisation, range, scale;  // scale = digitisation/range
     double offset_mean, offset_std, median_mean, median_std;
@@ -92,14 +94,14 @@ struct GenParams {
     int32_t ideal;        // SQ_IDEAL: per-read draws replaced by the means
     float amp_noise;
     uint32_t key0, key1;
-    uint32_t rk[20];      // the ten Philox round keys (k0 + r*W0, k1 + r*W1), precomputed
+    uint32_t rk[2 * PHILOX_ROUNDS];  // the Philox round keys (k0 + r*W0, k1 + r*W1), precomputed
     int64_t first_read;
     int32_t want_ss;
     int32_t shift_val;  // (int16)(30*digitisation/range)
-    K4Layout lay;       // shared-memory layout of the signal kernel for the launch's warp count
 };
 
 constexpr int K1_THREADS = 128;  // 4 tiles per CTA, one warp each
+constexpr int TK = 256;          // k-mers per tile at most (32 lanes x 8); also the row length of GenParams::dwells
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -109,29 +111,20 @@ __device__ __forceinline__ RngKey make_key(const GenParams &p, int read_local) {
     return RngKey{p.key0, p.key1, (uint32_t)r, (uint32_t)(r >> 32)};
 }
 
-// the j-th 16-bit draw (j in 0..7) of a Philox block: even draws are bits 1..16 of word j/2, odd draws bits 1..16 of
-// the same word rotated by 16.  Defined this way so that `word & 0x1FF82` is already the BYTE offset of the stratified
-// table entry (bit 0 of a binary16 offset is 0, bits 2-6 are the bank): no shift, no multiply in the sample loop.
-__device__ __forceinline__ uint32_t draw_word(const uint4 &w, int j) {  // j compile-time after unrolling
-    const uint32_t x = (j >> 1) == 0 ? w.x : (j >> 1) == 1 ? w.y : (j >> 1) == 2 ? w.z : w.w;
-    return (j & 1) ? __byte_perm(x, x, 0x1032) : x;  // rotate by 16
-}
-__device__ __forceinline__ uint32_t halfword(const uint4 &w, int j) { return (draw_word(w, j) >> 1) & 0xFFFFu; }
-// byte offset of the stratified table entry of a draw: ((h & 0xFFC1) | bank<<1) * 2
-__device__ __forceinline__ uint32_t draw_offset(uint32_t word, uint32_t bank4) { return (word & 0x1FF82u) | bank4; }
-
 // n / sps_fixed for tile-local sample numbers (exact: see GenParams::sps_magic)
 __device__ __forceinline__ uint32_t div_sps(const GenParams &p, uint32_t n) {
     return p.sps_fixed == 1 ? n : __umulhi(n, p.sps_magic);
 }
 
-__device__ __forceinline__ int find_seg(const SegDesc *__restrict__ segs, int n_segs, int tile) {
-    int lo = 0, hi = n_segs - 1;  // largest s with segs[s].tile0 <= tile
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&segs[mid].tile0) <= tile) lo = mid; else hi = mid - 1;
-    }
-    return lo;
+// ------------------------------------------------------------------------------------------------
+// init: the pore model indexed by (k+1)-mer.  Two consecutive k-mers of a read overlap in k-1 bases, so one 16-byte
+// entry addressed by the (k+1)-mer they span holds the parameters of both: the signal kernel's model gathers - one
+// 32-byte sector request each, the scarcest resource of its k-mer phase - are halved.  4^(k+1) x 16 B (16 MB for 9-mers).
+__global__ void __launch_bounds__(256) pair_model_kernel(const float2 *__restrict__ model, float4 *__restrict__ pair, uint32_t n_pair, uint32_t kmask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pair) return;
+    const float2 a = model[i >> 2], b = model[i & kmask];
+    pair[i] = make_float4(a.x, a.y, b.x, b.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +134,7 @@ __global__ void __launch_bounds__(256) tile_desc_kernel(const __grid_constant__ 
     if (si >= p.n_segs) return;
     const SegDesc seg = p.segs[si];
     const int64_t ss0 = p.reads[seg.read].ss_off + seg.k0;
+    const RngKey key = make_key(p, seg.read);
     const int nt = (seg.nk + p.T - 1) / p.T;
     for (int t = 0; t < nt; t++) {
         const int kstart = t * p.T;
@@ -152,37 +146,55 @@ __global__ void __launch_bounds__(256) tile_desc_kernel(const __grid_constant__ 
         d.read = seg.read;
         d.kidx0 = (uint32_t)(seg.k0_rng + kstart);
         d.ss_pos = ss0 + kstart;
-        d.B = 0;
-        d.pad = 0;
+        d.B = 0; d.S = 0; d.offset = 0.0; d.L = 0; d.pad = 0;
+        d.r_lo = key.r_lo; d.r_hi = key.r_hi;
+        d.pad2[0] = d.pad2[1] = 0;
         p.tiles[seg.tile0 + t] = d;
     }
 }
 
-// K1: per-tile sum of dwells (random-dwell modes only).  One warp per tile, one lane per Philox block of 8 k-mers.
-__global__ void __launch_bounds__(K1_THREADS) dwell_sum_kernel(const __grid_constant__ GenParams p) {
+// K1: the dwells (random-dwell modes only; src/gensig.c:255-256).  One warp per tile, one lane per Philox block of 8
+// k-mers: 8 table normals -> 8 dwells, stored as one 16-byte row piece of uint16 (k-mers beyond the tile get 0), the
+// tile's sample count, and - when asked for - the reference's aln->ss (src/gensig.c:273-281).
+__global__ void __launch_bounds__(K1_THREADS) dwell_kernel(const __grid_constant__ GenParams p) {
     const int tile = blockIdx.x * (K1_THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tile >= p.n_tiles) return;
-    const int nk_tile = p.tiles[tile].nk;
-    const RngKey key = make_key(p, p.tiles[tile].read);
+    const TileDesc *td = p.tiles + tile;
+    const int nk_tile = td->nk;
+    const RngKey key{p.key0, p.key1, td->r_lo, td->r_hi};
     uint32_t sum = 0;
+    uint32_t d[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) d[j] = 0;
     if (lane * 8 < nk_tile) {
-        const uint32_t blk = (p.tiles[tile].kidx0 >> 3) + lane;
-        const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
+        const uint32_t blk = (td->kidx0 >> 3) + lane;
+        const uint4 w = philox4x32_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
+        const int64_t ss0 = td->ss_pos + lane * 8;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float z = z16(p.z16, p.z2, stratify(halfword(w, j), blk), blk * 8 + j, key, ST_DWELL_TAIL);
-            const int d = dwell_from_z(z, p.dwell_mean, p.dwell_std);
-            if (lane * 8 + j < nk_tile) sum += (uint32_t)d;
+            const float z = z_global(p.z32, p.z2, z_offset(draw_word(w, j), (blk & 31u) << 2), blk * 8 + j, key, ST_DWELL_TAIL);
+            if (lane * 8 + j < nk_tile) {
+                d[j] = (uint32_t)dwell_from_z(z, p.dwell_mean, p.dwell_std);
+                if (p.want_ss) p.ss[ss0 + j] = (int32_t)d[j];
+            }
+            sum += d[j];
         }
     }
+    p.dwells[(size_t)tile * (TK / 8) + lane] = make_uint4(d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) p.tile_sum[tile] = sum;
 }
 
+// fixed-dwell modes with aln->ss requested: every k-mer has sps_fixed samples
+__global__ void __launch_bounds__(256) fixed_ss_kernel(const __grid_constant__ GenParams p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p.ss[i] = p.sps_fixed;
+}
+
 // ------------------------------------------------------------------------------------------------
-// K2: per read — scan its tiles, draw offset / median_before (src/gensig.c:312-318)
+// K2: per read — scan its tiles, draw offset / median_before (src/gensig.c:312-318), complete the tile descriptors
 template <bool RAND_DWELL>
 __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ GenParams p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,6 +215,7 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
                 p.tile_sum[tile] = sum;
             }
             p.tiles[tile].B = (uint32_t)total;
+            p.tiles[tile].S = sum;
             total += sum;
         }
         if (s == rd.seg0) n0 = (uint32_t)total;
@@ -216,21 +229,37 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
 
     double off = p.offset_mean, med = p.median_mean;
     if (!p.ideal) {
+        // one Philox block per read: draws 0-3 -> offset, 4-7 -> median_before, each a unit-norm mix of four table
+        // normals (weights: cos/sin products of 35, 40, 55 degrees); classes walk with the read index
         const RngKey key = make_key(p, r);
-        const uint4 w = philox4x32_10(0u, key.r_lo, key.r_hi, ST_READ, key.k0, key.k1);
-        const uint32_t ww[2] = {w.x, w.y};
+        const uint4 w = philox4x32(0u, key.r_lo, key.r_hi, ST_READ, key.k0, key.k1);
+        const double W4[4] = {0.6275068715971331, 0.43938504177070503, 0.3686878264946124, 0.5265407845183632};
         double z[2];
 #pragma unroll
         for (int d = 0; d < 2; d++) {
-            const float za = z16(p.z16, p.z2, ww[d] & 0xFFFFu, 2 * d, key, ST_READ_TAIL);
-            const float zb = z16(p.z16, p.z2, ww[d] >> 16, 2 * d + 1, key, ST_READ_TAIL);
-            z[d] = __dadd_rn(__dmul_rn((double)za, 0.8191520442889918), __dmul_rn((double)zb, 0.573576436351046));
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = 4 * d + u;
+                const float zz = z_global(p.z32, p.z2, z_offset(draw_word(w, j), ((8u * key.r_lo + j) & 31u) << 2), j, key, ST_READ_TAIL);
+                t[u] = __dmul_rn((double)zz, W4[u]);
+            }
+            z[d] = __dadd_rn(__dadd_rn(t[0], t[1]), __dadd_rn(t[2], t[3]));
         }
         off = __dadd_rn(__dmul_rn(z[0], p.offset_std), p.offset_mean);
         med = __dadd_rn(__dmul_rn(z[1], p.median_std), p.median_mean);
     }
     p.read_offset[r] = off;
     p.read_median[r] = med;
+    for (int s = rd.seg0; s < rd.seg0 + rd.nseg; s++) {
+        const SegDesc seg = p.segs[s];
+        const int ntile = (seg.nk + p.T - 1) / p.T;
+        for (int t = 0; t < ntile; t++) {
+            TileDesc *td = p.tiles + seg.tile0 + t;
+            td->offset = off;
+            td->L = (uint32_t)total;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -283,80 +312,47 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
 // K4: the signal kernel.
 //
 // Every WARP is autonomous: it owns a private tile buffer in shared memory and walks its own sequence of tiles,
-// alternating a k-mer phase (A: latency-bound — descriptor, base window, model gathers, warp scan) and a sample phase
-// (B: issue-bound — Philox, table normals, FFMA, 128-bit stores).  There are no CTA-wide barriers and no
-// producer/consumer hand-offs after the prologue; the 16-24 resident warps of an SM are at different points of their
+// alternating a k-mer phase (A: latency-bound — descriptor, base window, dwells, model gathers, warp scan) and a sample
+// phase (B: issue-bound — Philox, table normals, FFMA, 128-bit stores).  There are no CTA-wide barriers and no
+// producer/consumer hand-offs after the prologue; the 16 resident warps of an SM are at different points of their
 // tiles, so phase-A latency of some warps is covered by phase-B work of the others.  The CTA shares only read-only
-// tables: the binary16 quantile table and (when it fits) the pore model, both staged by TMA bulk copies, the boundary
-// LUT and the base-code table.
-//   phase A, lane = 8 consecutive k-mers = one Philox dwell block: 8 dwells, warp scan, chunk->k-mer map + boundary
-//            bitmap; digits -> ranks -> (mean,stdv) gathers -> (A',B') into par[]
+// tables: the 128 KB float quantile table staged by TMA bulk copies, the boundary LUT and the base-code table.
+//   phase A, lane = 8 consecutive k-mers: their dwells (one 16-byte load of what K1 drew), warp scan, chunk->k-mer map +
+//            boundary bitmap; digits -> ranks -> (mean,stdv) gathers -> (A', B'+32768) into par[]
 //   phase B, lane = one 16-byte chunk (8 samples) of the emitted signal per iteration: k-mer of the first sample from
-//            the map, the chunk's boundary byte -> LUT -> the 8 parameter addresses, one Philox block -> 8 table
-//            normals (bank-stratified lookups) -> FFMA -> cvt.rzi -> one 128-bit store
+//            the map, the parameters of that k-mer and the next two, the chunk's boundary byte -> predicates, one
+//            Philox block -> 8 table normals (bank-stratified lookups) -> fma.rz (+ predicated fma.rz for samples past
+//            a boundary) -> PRMT of the mantissas -> one 128-bit store
+//
+// Shared memory (byte offsets into the dynamic array, all compile-time so that they fold into LDS/STS immediates):
+//   [par: one TK x float2 array per warp]  [Z32: 128 KB]  [code: 256 B]  [mbar]  [per warp: map MAPC u8, bmap MAPC u8, digits]
 
-constexpr int K4_MAX_WARPS = 24;
-constexpr int K4_MAX_THREADS = K4_MAX_WARPS * 32;  // register budget: 65536 / 768 = 85
-constexpr int TK = 256;      // k-mers per tile (32 lanes x 8)
-constexpr int MAPC = 1344;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8 (dna-r10: 256 k-mers x 40)
-constexpr int DIG_BYTES = TK + 32;
-constexpr int LUT_COPIES = 4;
-constexpr int NCHUNK = 1;    // 16-byte chunks per lane per phase-B iteration (more = more ILP but more code)
-constexpr int WARP_TILE_BYTES = TK * 8 + 2 * MAPC + DIG_BYTES;  // par + map + bmap + digits
+#ifndef SQG_K4_WARPS
+#define SQG_K4_WARPS 16
+#endif
+constexpr int K4_WARPS = SQG_K4_WARPS;
+constexpr int K4_THREADS = K4_WARPS * 32;  // register budget: 65536 / 512 = 128
+constexpr int MAPC = 1344;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8 (dna-r10: 256 k-mers x 37)
+constexpr int DIG_BYTES = TK + 32;   // digits of the tile's base window; the same size holds the raw window (16-byte granules)
+// per-warp buffer
+constexpr uint32_t W_MAP = 0;                        // chunk -> k-mer of its first sample (u8)
+constexpr uint32_t W_BMAP = W_MAP + MAPC;            // chunk -> bit j: a k-mer starts at its sample j
+constexpr uint32_t W_DIG = W_BMAP + MAPC;            // base digits
+constexpr uint32_t W_RAW = W_DIG + DIG_BYTES;        // prefetched base window (ASCII), 16-byte granules
+constexpr uint32_t W_DWELL = W_RAW + DIG_BYTES;      // prefetched dwells of the tile: TK x uint16
+constexpr uint32_t W_DESC = W_DWELL + TK * 2;        // two TileDesc slots
+constexpr uint32_t W_SIGOFF = W_DESC + 2 * 80;       // two int64 slots
+constexpr uint32_t WARP_BYTES = W_SIGOFF + 16;
+constexpr uint32_t SM_PAR = 0;
+constexpr uint32_t SM_Z = SM_PAR + K4_WARPS * TK * 8;          // (128-byte aligned)
+constexpr uint32_t SM_CODE = SM_Z + Z32_BYTES;
+constexpr uint32_t SM_MBAR = SM_CODE + 256;
+constexpr uint32_t SM_WARP = SM_MBAR + 16;
+constexpr uint32_t SM_TOTAL = SM_WARP + K4_WARPS * WARP_BYTES;
+static_assert(SM_Z % 128 == 0 && SM_WARP % 16 == 0 && WARP_BYTES % 16 == 0 && MAPC % 16 == 0 && DIG_BYTES % 16 == 0, "alignment");
+static_assert(SM_TOTAL <= 232448, "227 KB of shared memory per CTA");
 
-// Shared-memory layout (dynamic), for nw warps:
-//   [par: nw*TK float2]  (first, so that parameter addresses fit 16 bits)   [map: nw*MAPC u8] [bmap: nw*MAPC u8]
-//   [digit: nw*DIG_BYTES u8] [lut: 128*LUT_COPIES uint4] [code: 256 u8] [mbar: 8 B, 16-aligned]
-//   [Z16: 128 KB, 128-aligned, if USE_Z] [model: num_kmer*8 B if MODEL_SMEM]
-__host__ __device__ inline K4Layout k4_layout(int nw, bool use_z, uint32_t model_bytes) {
-    K4Layout L;
-    uint32_t o = 0;
-    L.par = o; o += (uint32_t)nw * TK * 8;
-    L.map = o; o += (uint32_t)nw * MAPC;
-    L.bmap = o; o += (uint32_t)nw * MAPC;
-    L.digit = o; o += (uint32_t)nw * DIG_BYTES;
-    o = (o + 15u) & ~15u;
-    L.lut = o; o += 128 * LUT_COPIES * 16;
-    L.code = o; o += 256;
-    L.mbar = o; o += 16;
-    o = (o + 127u) & ~127u;
-    L.z16 = o; o += use_z ? (uint32_t)Z16_N * 2 : 0;
-    L.model = o; o += model_bytes;
-    L.total = o;
-    return L;
-}
-
-// ---- raw shared-memory access by 32-bit shared address ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float lds_half(uint32_t addr) {
-    unsigned short h;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
-    return __half2float(__ushort_as_half(h));
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void sts_zero16(uint32_t addr) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void atoms_or(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // ---- mbarrier / TMA bulk copy for the one-time table staging (SASS: SYNCS, UBLKCP) ----
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar) {
@@ -384,256 +380,422 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t par
         "r"(parity)
         : "memory");
 }
+// ---- per-lane asynchronous global -> shared copies (SASS: LDGSTS) for the next tile's inputs ----
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+// shared-window address of a pointer, computed behind an opaque asm: the compiler must not tie the (vector-register)
+// addresses of the asynchronous copies to the base of the ordinary shared-memory accesses, which it keeps in a uniform
+// register ([R + UR + imm] addressing in the sample loop)
+__device__ __forceinline__ uint32_t opaque_smem_addr(const void *sptr) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(sptr));
+    return a;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void st_cs_v4(void *gptr, uint4 v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- shared-memory loads of the sample loop, by absolute shared-window address with the constant part as an
+// immediate.  The dynamic array starts right after the driver's reserved kilobyte (cudaDevAttrReservedSharedMemoryPerBlock;
+// this kernel has no static shared memory), so `offset + SMEM_ORIGIN + constant` needs no base register: one LOP3 makes
+// the table offset and the load takes it as is.  The kernel prologue checks the origin and refuses to run otherwise. ----
+constexpr uint32_t SMEM_ORIGIN = 0x400;
+template <uint32_t IMM>
+__device__ __forceinline__ float lds_f32(uint32_t off) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+    return v;
+}
+template <uint32_t IMM>
+__device__ __forceinline__ float2 lds_f2(uint32_t off) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+    return v;
+}
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t off) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+    return v;
+}
 
 // What phase B needs to know about the tile (registers, warp-uniform)
-struct TileHdr {
+struct TileCtx {
     uint32_t S;      // samples in the tile
     uint32_t ph;     // chunk w covers tile samples [8w-ph, 8w-ph+8)
-    uint32_t B;      // first logical sample of the tile within the read
-    uint32_t L;      // samples in the read
+    uint32_t C0;     // emitted chunk (= Philox block) of the tile's chunk 0; chunk w is C0+w, or C0-w when reversed
     uint32_t r_lo, r_hi;  // global read index (Philox counter words 1,2)
     int16_t *out;    // start of the read in the signal arena
 };
 
 // ---- phase B ---------------------------------------------------------------------------------------------------
 
-// 32-bit shared addresses of a warp's tile buffer and of the CTA's tables, computed once per kernel
-struct WarpSmem {
-    uint32_t par, map, bmap, dig, lut, z;
-};
-
-// NCH chunks of the same lane (w, w+32, ...) in one straight-line block so that their Philox chains and table
-// lookups interleave (instruction-level parallelism: a warp alone sustains ~2x the issue rate).
-template <bool NOISY, bool RAND_DWELL, bool REV, int NCH>
-__device__ __forceinline__ void emit_chunks_fast(const GenParams &p, const WarpSmem &ws, const TileHdr &h, int lane,
-                                                 const uint32_t (&wv)[NCH], const bool (&st)[NCH]) {
-    const uint32_t zbase = ws.z;
-    const uint32_t par_addr = ws.par;  // < 64 KB by layout
-    uint32_t q0[NCH], pa[NCH][4], v[NCH][8];
-#pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        const uint32_t wc = wv[c];
-        const int s0 = (int)(8 * wc) - (int)h.ph;  // first tile sample of the chunk; < 0 only for a clipped chunk 0
-        q0[c] = REV ? (h.L - h.B - (uint32_t)(s0 + 8)) : (h.B + (uint32_t)s0);  // emitted position, multiple of 8
-        uint32_t k0, bm;
-        if (RAND_DWELL) {
-            k0 = lds_u8(ws.map + wc);
-            bm = lds_u8(ws.bmap + wc) >> 1;  // (k-mer 0's own start is never marked: it is not a boundary to cross)
-        } else {
-            k0 = div_sps(p, (uint32_t)max(s0, 0));
-            bm = 0;
-            for (int b = (int)((k0 + 1) * (uint32_t)p.sps_fixed) - s0; b < 8; b += p.sps_fixed) bm |= 1u << (b - 1);
-        }
-        const uint4 lu = lds_u4(ws.lut + (bm * LUT_COPIES + (lane & (LUT_COPIES - 1))) * 16);
-        const uint32_t rep = (k0 * 8 + par_addr) * 0x00010001u;
-        pa[c][0] = lu.x + rep; pa[c][1] = lu.y + rep; pa[c][2] = lu.z + rep; pa[c][3] = lu.w + rep;
-    }
-    if (NOISY) {
-        uint32_t rw[NCH][4];
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const uint4 r4 = philox4x32_10_rk(q0[c] >> 3, h.r_lo, h.r_hi, ST_AMP, p.rk);
-            rw[c][0] = r4.x; rw[c][1] = r4.y; rw[c][2] = r4.z; rw[c][3] = r4.w;
-        }
-        float zmax = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const uint32_t bank4 = (q0[c] >> 1) & 0x7Cu;  // stratify(): (block & 31) << 2, the chunk's Philox block picks the bank
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int e = REV ? 7 - j : j;  // slot in the emitted chunk = which 16-bit draw
-                const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
-                const uint32_t x = (e & 1) ? __byte_perm(rw[c][e >> 1], rw[c][e >> 1], 0x1032) : rw[c][e >> 1];
-                const float z = lds_half(zbase + draw_offset(x, bank4));
-                zmax = fmaxf(zmax, fabsf(z));
-                v[c][e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
-            }
-        }
-        if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
-            // rare: some draw fell into one of the 16 outermost cells -> refine it (13 more bits)
-            const RngKey key{p.key0, p.key1, h.r_lo, h.r_hi};
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const uint32_t bank4 = (q0[c] >> 1) & 0x7Cu;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int e = REV ? 7 - j : j;
-                    const uint32_t x = (e & 1) ? __byte_perm(rw[c][e >> 1], rw[c][e >> 1], 0x1032) : rw[c][e >> 1];
-                    const uint32_t hw = draw_offset(x, bank4) >> 1;
-                    if ((hw & 0x7FFFu) >= Z_TAIL_FIRST) {
-                        const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
-                        const float z = z16_tail(p.z2, hw, q0[c] + e, key, ST_AMP_TAIL);
-                        v[c][e] = (uint32_t)__float2int_rz(fmaf(z, ab.x, ab.y));
-                    }
-                }
-            }
-        }
+// k-mer of a chunk's first sample and the boundary mask (bit j, 1..7: a k-mer starts at tile-order slot j)
+template <bool RAND_DWELL>
+__device__ __forceinline__ void chunk_kmers(const GenParams &p, const unsigned char *smem, uint32_t map_off, const TileCtx &t, uint32_t w,
+                                            uint32_t &k0, uint32_t &m1) {
+    if (RAND_DWELL) {
+        k0 = smem[map_off + W_MAP + w];
+        m1 = smem[map_off + W_BMAP + w] & 0xFEu;  // (a start on the chunk's first sample is not a boundary to cross)
     } else {
-#pragma unroll
-        for (int c = 0; c < NCH; c++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int e = REV ? 7 - j : j;
-                const float2 ab = lds_f2((j & 1) ? (pa[c][j >> 1] >> 16) : (pa[c][j >> 1] & 0xFFFFu));
-                v[c][e] = __float_as_uint(ab.y);
-            }
+        const int s0 = (int)(8 * w) - (int)t.ph;
+        k0 = div_sps(p, (uint32_t)max(s0, 0));
+        m1 = 0;
+        for (int b = (int)((k0 + 1) * (uint32_t)p.sps_fixed) - s0; b < 8; b += p.sps_fixed) m1 |= 1u << b;
     }
+}
+
+// The exact path of one chunk, start to finish (rare: a clipped chunk at an end of the tile, a chunk with a flagged
+// sample - tail cell of the table, negative value, value beyond int16 - or with four or more k-mers, and every chunk in
+// wide mode): samples are trunc(fma.rz(z, A', Bq)) with the tail cells refined and any number of boundaries; only the
+// tile's own samples are stored (the neighbouring tile computes the same Philox block and stores the rest).
+// par[] holds B'+32768 (or Bq itself in wide mode).
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char *smem, TileCtx t, uint32_t par_off, uint32_t map_off,
+                                         uint32_t w) {
+    uint32_t k0, m1;
+    chunk_kmers<RAND_DWELL>(p, smem, map_off, t, w, k0, m1);
+    const uint32_t par0 = k0 * 8 + par_off;
+    const uint32_t Cq = REV ? t.C0 - w : t.C0 + w;
+    const uint32_t class4 = (Cq & 31u) << 2;
+    const RngKey key{p.key0, p.key1, t.r_lo, t.r_hi};
+    uint4 r4 = make_uint4(0, 0, 0, 0);
+    if (NOISY) r4 = philox4x32_rk(Cq, t.r_lo, t.r_hi, ST_AMP, p.rk);
+    const float sub = p.wide ? 0.f : SAMPLE_MAGIC;
+    int16_t *dst = t.out + (size_t)Cq * 8;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
-        const uint4 pk = make_uint4(__byte_perm(v[c][0], v[c][1], 0x5410), __byte_perm(v[c][2], v[c][3], 0x5410),
-                                    __byte_perm(v[c][4], v[c][5], 0x5410), __byte_perm(v[c][6], v[c][7], 0x5410));
-        if (st[c]) {
-            const int s0 = (int)(8 * wv[c]) - (int)h.ph;
-            if (s0 >= 0 && (uint32_t)(s0 + 8) <= h.S) {
-                __stcs(reinterpret_cast<uint4 *>(h.out + q0[c]), pk);
+    for (int e = 0; e < 8; e++) {
+        const int j = REV ? 7 - e : e;
+        if (8 * w + j - t.ph < t.S) {
+            const float2 ab = *reinterpret_cast<const float2 *>(smem + par0 + 8 * __popc(m1 & ((2u << j) - 1u)));
+            uint32_t v;
+            if (NOISY) {
+                const uint32_t off = z_offset(draw_word(r4, e), class4);
+                float z = *reinterpret_cast<const float *>(smem + SM_Z + off);
+                if (z_is_tail(off)) z = z_tail(p.z2, off, Cq * 8 + e, key, ST_AMP_TAIL);
+                v = sample_exact(z, ab.x, __fsub_rn(ab.y, sub));
             } else {
-                // clipped chunk at an end of the tile (at most two per tile): store only the tile's own samples; the
-                // neighbouring tile computes the same Philox block and stores the rest
-                const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int e = REV ? 7 - j : j;
-                    // (uint32_t)(s0 + j) < S also rejects the negative positions of a clipped first chunk
-                    if ((uint32_t)(s0 + j) < h.S) h.out[q0[c] + e] = (int16_t)((e & 1) ? (pw[e >> 1] >> 16) : pw[e >> 1]);
-                }
+                v = __float_as_uint(ab.y);
             }
+            dst[e] = (int16_t)v;
         }
     }
 }
 
+// One chunk = 8 consecutive samples = at most 3 k-mers on the fast path: the parameters of k-mers k0, k0+1, k0+2 are
+// loaded once (three 8-byte loads) and every sample picks its own by PREDICATE - the k-mer boundaries inside the
+// chunk arrive as a bit mask, `mask-1` has its bits clear exactly from the first boundary upwards, and one R2P moves
+// seven of those bits into predicate registers - so a sample costs one FFMA plus at most two predicated ones on the
+// FMA pipe, and no shared-memory traffic of its own.  The loop body has no rare path inside: a lane only notes which
+// of its chunks needs the exact path (flagged sample, 4+ k-mers) and redoes it after the loop.
 template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __forceinline__ void emit_tile(const GenParams &p, const WarpSmem &ws, const TileHdr h, int lane) {
-    const uint32_t nW = (h.S + h.ph + 7) >> 3;  // chunks touched by the tile (the first and last may be clipped)
-    for (uint32_t w = lane; w < nW; w += 32 * NCHUNK) {
-        uint32_t wv[NCHUNK];
-        bool st[NCHUNK];
-#pragma unroll
-        for (int c = 0; c < NCHUNK; c++) {
-            st[c] = w + 32u * c < nW;
-            wv[c] = st[c] ? w + 32u * c : w;  // a missing partner is computed redundantly and not stored
+__device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned char *smem, const TileCtx t, int lane, uint32_t par_off,
+                                          uint32_t map_off) {
+    const uint32_t nW = (t.S + t.ph + 7) >> 3;      // chunks touched by the tile (the first and last may be clipped)
+    const uint32_t w_lo = (t.ph + 7) >> 3;          // chunks [w_lo, w_hi) lie wholly inside the tile
+    const uint32_t w_hi = (t.S + t.ph) >> 3;
+    if (NOISY && p.wide) {
+        for (uint32_t w = lane; w < nW; w += 32) exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, par_off, map_off, w);
+        return;
+    }
+    const uint32_t class4 = ((REV ? t.C0 - (uint32_t)lane : t.C0 + (uint32_t)lane) & 31u) << 2;  // same for all chunks of a lane
+    uint32_t n_redo = 0, w_redo = 0;
+    // Software pipeline, one chunk deep: the Philox block and the map bytes of the lane's NEXT chunk are produced while
+    // the table lookups and FFMAs of the current one are in flight (two independent dependency chains per warp).
+    uint4 r4n = make_uint4(0, 0, 0, 0);
+    uint32_t k0n = 0, m1n = 0;
+    {
+        const uint32_t w = lane;
+        if (NOISY) r4n = philox4x32_rk(REV ? t.C0 - w : t.C0 + w, t.r_lo, t.r_hi, ST_AMP, p.rk);
+        if (RAND_DWELL) { k0n = lds_u8<W_MAP>(map_off + w); m1n = lds_u8<W_BMAP>(map_off + w); }
+    }
+    for (uint32_t wb = 0; wb < nW; wb += 32) {   // wb is warp-uniform: 32 consecutive chunks per iteration
+        const uint32_t w = wb + lane;
+        if (w >= nW) break;
+        const uint4 r4 = r4n;
+        uint32_t k0 = k0n, m1 = m1n & 0xFEu;  // (a start on the chunk's first sample is not a boundary to cross)
+        {
+            const uint32_t wn = w + 32;  // (past the tile's end for the last one: computed, never used)
+#ifdef SQG_KO_PHILOX
+            if (NOISY) r4n = make_uint4(wn * 0x9E3779B9u, wn * 0x85EBCA6Bu, wn * 0xC2B2AE35u, wn * 0x27D4EB2Fu);
+#else
+            if (NOISY) r4n = philox4x32_rk(REV ? t.C0 - wn : t.C0 + wn, t.r_lo, t.r_hi, ST_AMP, p.rk);
+#endif
+            if (RAND_DWELL) { k0n = lds_u8<W_MAP>(map_off + wn); m1n = lds_u8<W_BMAP>(map_off + wn); }
         }
-        emit_chunks_fast<NOISY, RAND_DWELL, REV, NCHUNK>(p, ws, h, lane, wv, st);
+        if (!RAND_DWELL) chunk_kmers<RAND_DWELL>(p, smem, map_off, t, w, k0, m1);
+        const uint32_t par0 = k0 * 8 + par_off;
+        const float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0), q2 = lds_f2<16>(par0);
+        const uint32_t t1 = m1 - 1u;        // bit j clear  <=>  slot j lies at or after the 1st boundary
+        const uint32_t m2 = m1 & t1;        // boundaries after the first
+        const uint32_t t2 = m2 - 1u;        // bit j clear  <=>  slot j lies at or after the 2nd boundary
+        const uint32_t m3 = m2 & t2;        // non-zero: a 3rd boundary -> exact path
+        const uint32_t Cq = REV ? t.C0 - w : t.C0 + w;
+        uint4 pk;
+        uint32_t bad;
+        if (NOISY) {
+            float zz[8], v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {   // e = slot in the emitted chunk = which draw; j = slot in tile order
+#ifdef SQG_KO_Z
+                zz[e] = __uint_as_float((z_offset(draw_word(r4, e), class4) & 0x7FFFFFu) | 0x3F000000u);
+#else
+                zz[e] = lds_f32<SM_Z>(z_offset(draw_word(r4, e), class4));
+#endif
+                v[e] = fma_rz(zz[e], q0.x, q0.y);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {   // level by level, so that one R2P per level sets the predicates
+                const int j = REV ? 7 - e : e;
+                if (j >= 1 && !(t1 & (1u << j))) v[e] = fma_rz(zz[e], q1.x, q1.y);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int j = REV ? 7 - e : e;
+                if (j >= 2 && !(t2 & (1u << j))) v[e] = fma_rz(zz[e], q2.x, q2.y);
+            }
+            uint32_t u[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) u[e] = __float_as_uint(v[e]);
+            // bits 8..23 of each float, packed little-endian
+            pk = make_uint4(__byte_perm(u[0], u[1], 0x6521), __byte_perm(u[2], u[3], 0x6521),
+                            __byte_perm(u[4], u[5], 0x6521), __byte_perm(u[6], u[7], 0x6521));
+            bad = ((pk.x | pk.y | pk.z | pk.w) & 0x80008000u) | m3;
+        } else {
+            uint32_t v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int j = REV ? 7 - e : e;
+                float x = q0.y;
+                if (j >= 1 && !(t1 & (1u << j))) x = q1.y;
+                if (j >= 2 && !(t2 & (1u << j))) x = q2.y;
+                v[e] = __float_as_uint(x);
+            }
+            // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
+            pk = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
+                            __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
+            bad = m3;
+        }
+        int16_t *dst = t.out + (size_t)Cq * 8;
+#ifdef SQG_KO_STORE
+        if (pk.x == 0x12345678u && pk.y == 0x9abcdef0u) st_cs_v4(dst, pk);
+        if (bad != 0) { n_redo++; w_redo = w; }
+        continue;
+#endif
+        if (wb >= w_lo && wb + 32 <= w_hi) {   // (uniform) every chunk of this iteration lies wholly inside the tile
+            st_cs_v4(dst, pk);
+        } else if (w - w_lo < w_hi - w_lo) {
+            st_cs_v4(dst, pk);
+        } else {
+            // clipped chunk at an end of the tile (at most two per tile): store only the tile's own samples; the
+            // neighbouring tile computes the same Philox block and stores the rest
+            const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int j = REV ? 7 - e : e;
+                if (8 * w + j - t.ph < t.S) dst[e] = (int16_t)((e & 1) ? (pw[e >> 1] >> 16) : pw[e >> 1]);
+            }
+        }
+        if (bad != 0) { n_redo++; w_redo = w; }
+    }
+    if (__builtin_expect(n_redo != 0, 0)) {
+        if (n_redo == 1) {
+            exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, par_off, map_off, w_redo);
+        } else {
+            for (uint32_t w = lane; w < nW; w += 32) exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, par_off, map_off, w);
+        }
     }
 }
 
 // ---- phase A ---------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ TileDesc load_tile_desc(const TileDesc *__restrict__ tiles, int tile) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(tiles + tile);
-    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    TileDesc d;
-    d.a_off = (int64_t)(((uint64_t)a.y << 32) | a.x);
-    d.b_off = (int64_t)(((uint64_t)a.w << 32) | a.z);
-    d.a_rem = (int32_t)b.x; d.nk = (int32_t)b.y; d.read = (int32_t)b.z; d.kidx0 = b.w;
-    d.ss_pos = (int64_t)(((uint64_t)c.y << 32) | c.x);
-    d.B = c.z; d.pad = 0;
-    return d;
+__device__ __forceinline__ TileDesc read_tile_desc(const unsigned char *smem, uint32_t off) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(smem + off);
+    const uint4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+    TileDesc t;
+    t.a_off = (int64_t)(((uint64_t)a.y << 32) | a.x);
+    t.b_off = (int64_t)(((uint64_t)a.w << 32) | a.z);
+    t.a_rem = (int32_t)b.x; t.nk = (int32_t)b.y; t.read = (int32_t)b.z; t.kidx0 = b.w;
+    t.ss_pos = (int64_t)(((uint64_t)c.y << 32) | c.x);
+    t.B = c.z; t.S = c.w;
+    t.offset = __longlong_as_double((long long)(((uint64_t)d.y << 32) | d.x));
+    t.L = d.z; t.pad = 0;
+    t.r_lo = e.x; t.r_hi = e.y; t.pad2[0] = t.pad2[1] = 0;
+    return t;
 }
 
-constexpr int WIN_LOADS = (TK + 8 + 31) / 32;  // byte loads per lane for a tile's base window (k <= 9)
+constexpr int WIN_LOADS = (TK + 8 + 31) / 32;  // bytes per lane of a tile's base window (k <= 9)
 
-// Source order = latency order: global loads first (base window, per-read values), then the dwell draws (shared
-// memory only) while they fly, then digits -> ranks -> model gathers, then the map/bitmap scatter while the gathers fly.
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
-__device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDesc td, int lane, const WarpSmem &ws,
-                                                const uint8_t *dig, const uint8_t *code, const float2 *__restrict__ model) {
+// a tile whose base window straddles the two pieces of its segment (only around a --prefix junction)
+__device__ __forceinline__ bool tile_is_junction(const GenParams &p, int32_t a_rem, int32_t nk) {
+    return a_rem > 0 && a_rem < nk + p.k - 1;
+}
+
+// Asynchronous fetch of a tile's inputs into the warp's buffer: the base window as 16-byte granules (the aligned
+// superset of the window), its dwells, its read's arena offset.  `desc_off` = the tile's descriptor, already in smem.
+template <bool RAND_DWELL>
+__device__ __forceinline__ void fetch_tile_inputs(const GenParams &p, const unsigned char *smem, uint32_t wbase, uint32_t map_off,
+                                                  uint32_t desc_off, uint32_t sigoff_off, int tile, int lane) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(smem + desc_off);
+    const uint4 b = *reinterpret_cast<const uint4 *>(smem + desc_off + 16);
+    const int32_t a_rem = (int32_t)b.x, nk = (int32_t)b.y, read = (int32_t)b.z;
+    if (!tile_is_junction(p, a_rem, nk)) {
+        const int64_t off = a_rem > 0 ? (int64_t)(((uint64_t)a.y << 32) | a.x) : (int64_t)(((uint64_t)a.w << 32) | a.z);
+        const uint8_t *g = p.bases + off;
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+        const uint32_t nbytes = shift + (uint32_t)(nk + p.k - 1);
+        if ((uint32_t)lane * 16 < nbytes) cp_async16(wbase + W_RAW + lane * 16, g - shift + lane * 16);
+    }
+    if (RAND_DWELL) cp_async16(wbase + W_DWELL + lane * 16, p.dwells + (size_t)tile * (TK / 8) + lane);
+    if (lane == 0) cp_async8(wbase + (sigoff_off - map_off), p.read_sigoff + read);
+}
+__device__ __forceinline__ void fetch_tile_desc(const GenParams &p, uint32_t wbase, uint32_t desc_rel, int tile, int lane) {
+    if (lane < 5) cp_async16(wbase + desc_rel + lane * 16, reinterpret_cast<const uint4 *>(p.tiles + tile) + lane);
+}
+
+// Phase A of one tile.  Its descriptor, base window, dwells and arena offset are already in the warp's buffer.
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
+__device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, unsigned char *smem, uint32_t par_off, uint32_t map_off,
+                                                uint32_t desc_off, uint32_t sigoff_off) {
+    const TileDesc td = read_tile_desc(smem, desc_off);
     const int nk_tile = td.nk;
-    // (1) the tile's base window: coalesced byte loads, all in flight at once
-    uint32_t raw[WIN_LOADS];
     const int nb = nk_tile + p.k - 1;
-    const uint8_t *pa_lane = p.bases + td.a_off + lane, *pb_lane = p.bases + td.b_off + lane;
-    if (td.a_rem >= nb || td.a_rem <= 0) {  // the whole window lies in one piece (always, except around a prefix junction)
-        const uint8_t *src = td.a_rem > 0 ? pa_lane : pb_lane;
-#pragma unroll
-        for (int u = 0; u < WIN_LOADS; u++) raw[u] = (lane + 32 * u < nb) ? __ldg(src + 32 * u) : 0u;
-    } else {
+    const uint32_t dig_off = map_off + W_DIG;
+    const uint32_t B = td.B, L = td.L, S = td.S;
+    const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
+    const int m0 = lane * 8;
+
+    // (1) bases -> digits (the code table folds IUPAC letters, src/seq.h:14-28 / :45-60)
+    if (!tile_is_junction(p, td.a_rem, nk_tile)) {
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
+        const uint32_t raw_off = map_off + W_RAW + shift + lane;
 #pragma unroll
         for (int u = 0; u < WIN_LOADS; u++) {
             const int i = lane + 32 * u;
-            raw[u] = (i < nb) ? __ldg((i < td.a_rem ? pa_lane : pb_lane) + 32 * u) : 0u;
-        }
-    }
-    // (2) per-read values
-    const uint32_t L = __ldg(p.read_siglen + td.read);
-    const double offset = __ldg(p.read_offset + td.read);
-    const int64_t sigoff = __ldg(p.read_sigoff + td.read);
-    const RngKey key = make_key(p, td.read);
-    const uint32_t B = td.B;
-    const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
-    const int m0 = lane * 8;
-    const bool active = m0 < nk_tile;
-
-    // (3) dwells of this lane's 8 k-mers = one Philox block (src/gensig.c:255-256), then the warp scan
-    int d[8];
-    uint32_t o = 0, S = (uint32_t)nk_tile * (uint32_t)p.sps_fixed;
-    if (RAND_DWELL) {
-        const uint32_t blk = (td.kidx0 >> 3) + lane;
-        const uint4 w = philox4x32_10_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
-        const uint32_t zbase = ws.z;
-        float zmax = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float z = lds_half(zbase + draw_offset(draw_word(w, j), (blk & 31u) << 2));
-            zmax = fmaxf(zmax, fabsf(z));
-            d[j] = dwell_from_z(z, p.dwell_mean, p.dwell_std);
-        }
-        if (__builtin_expect(zmax >= Z_TAIL_THR, 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t hw = stratify(halfword(w, j), blk);
-                if ((hw & 0x7FFFu) >= Z_TAIL_FIRST)
-                    d[j] = dwell_from_z(z16_tail(p.z2, hw, blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
+            if (i < nb) {
+                const uint32_t c = smem[SM_CODE + smem[raw_off + 32 * u]];
+                smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
             }
         }
-        if (nk_tile < TK) {  // only the last tile of a segment has lanes beyond its end
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (m0 + j >= nk_tile) d[j] = 0;
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < nb; i += 32) {
+            const uint32_t c = smem[SM_CODE + __ldg(p.bases + (i < td.a_rem ? td.a_off : td.b_off) + i)];
+            smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
         }
-        uint32_t local = 0;
+    }
+
+    // (2) warp scan of the dwells, then the chunk -> k-mer map and the boundary bitmap
+    if (RAND_DWELL) {
+        static_assert(MAPC / 16 <= 96, "three 16-byte stores per lane must cover the boundary bitmap");
+        const uint4 dq = *reinterpret_cast<const uint4 *>(smem + map_off + W_DWELL + lane * 16);
 #pragma unroll
-        for (int j = 0; j < 8; j++) local += (uint32_t)d[j];
+        for (int u = 0; u < 3; u++)
+            if (lane + 32 * u < MAPC / 16) *reinterpret_cast<uint4 *>(smem + map_off + W_BMAP + 16 * (lane + 32 * u)) = make_uint4(0, 0, 0, 0);
+        const uint32_t t4 = dq.x + dq.y + dq.z + dq.w;  // packed halves: no carry, every dwell < 2^14
+        const uint32_t local = (t4 & 0xFFFFu) + (t4 >> 16);
         uint32_t inc = local;
 #pragma unroll
         for (int sh = 1; sh < 32; sh <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, inc, sh);
             if (lane >= sh) inc += v;
         }
-        S = __shfl_sync(0xffffffffu, inc, 31);
-        o = inc - local;
+        __syncwarp();
+        const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
+        uint32_t pos = inc - local + ph;  // the k-mer starts at bit (pos&7) of chunk (pos>>3)
+        uint32_t wprev = lane == 0 ? 0u : (pos + 7) >> 3;  // (chunk 0's clipped first sample falls into k-mer 0)
+        const uint32_t pos0 = pos, wprev0 = wprev;
+        uint32_t long_dwell = 0;   // becomes >= 4 when some k-mer owns the first sample of more than three chunks
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t dj = (j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xFFFFu);
+            const uint32_t m = (uint32_t)(m0 + j);
+            const uint32_t end = pos + dj;
+            const uint32_t wnext = (end + 7) >> 3;
+            // chunks [wprev, wnext) have their first sample inside this k-mer
+            const uint32_t n = wnext - wprev;
+            unsigned char *mp = smem + map_off + W_MAP + wprev;
+#ifdef SQG_KO_MAP
+            if (n > 1000) mp[0] = (unsigned char)m;
+            long_dwell |= n;
+            pos = end; wprev = wnext;
+            continue;
+#endif
+            if (n > 0) mp[0] = (unsigned char)m;
+            if (n > 1) mp[1] = (unsigned char)m;
+            if (n > 2) mp[2] = (unsigned char)m;
+            long_dwell |= n;
+            if (dj != 0 && m != 0)
+                atomicOr(reinterpret_cast<uint32_t *>(smem + map_off + W_BMAP + ((pos >> 5) << 2)), 1u << (pos & 31u));
+            pos = end;
+            wprev = wnext;
+        }
+        if (__builtin_expect(long_dwell > 3, 0)) {   // rare (dwell >= 25 samples): the remaining chunks of such k-mers
+            uint32_t ps = pos0, wp = wprev0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t dj = (j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xFFFFu);
+                const uint32_t wn = (ps + dj + 7) >> 3;
+                for (uint32_t c = wp + 3; c < wn; c++) smem[map_off + W_MAP + c] = (unsigned char)(m0 + j);
+                ps += dj;
+                wp = wn;
+            }
+        }
     } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) d[j] = (m0 + j < nk_tile) ? p.sps_fixed : 0;
+        __syncwarp();
     }
 
-    // (4) bases -> digits (the code table folds IUPAC letters, src/seq.h:14-28 / :45-60)
-#pragma unroll
-    for (int u = 0; u < WIN_LOADS; u++) {
-        const int i = lane + 32 * u;
-        const uint32_t c = code[raw[u] & 0xFFu];
-        if (i < nb) sts_u8(ws.dig + i, METH ? (c >> 4) : (c & 3u));
-    }
-    __syncwarp();
-
-    // (5) ranks of this lane's 8 k-mers (src/seq.h:31-42 / :62-74).  They are visited in ROTATED order
-    // jj(j) = (j + lane/2) & 7 so that the 8-byte parameter stores of a half-warp fall into 16 different bank pairs.
-    const int rot = METH ? 0 : (lane >> 1);
-    uint32_t ranks[8];
+    // (3) ranks of this lane's 8 k-mers (src/seq.h:31-42 / :62-74), (4) their parameters from (level_mean, level_stdv)
+    const float scale_f = (float)p.scale, off_f = (float)td.offset;
+    auto make_par = [&](float mean, float stdv) -> float2 {
+        if (NOISY) {
+            // single precision, rounded once each: A' = (stdv*amp_noise)*scale, B' = fma(mean, scale, -offset), then
+            // B' + 32768 (the sample arithmetic's magic offset; wide mode keeps Bq = (B' + 32768) - 32768 itself)
+            const float Bm = __fadd_rn(fmaf(mean, scale_f, -off_f), SAMPLE_MAGIC);
+            return make_float2(__fmul_rn(__fmul_rn(stdv, p.amp_noise), scale_f), p.wide ? __fsub_rn(Bm, SAMPLE_MAGIC) : Bm);
+        } else {
+            // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
+            const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mean, p.digitisation), p.range), td.offset);
+            return make_float2(0.f, __uint_as_float(to_i16_bits(v)));
+        }
+    };
     {
-        const uint2 dwa = *reinterpret_cast<const uint2 *>(dig + m0);
-        const uint2 dwb = *reinterpret_cast<const uint2 *>(dig + m0 + 8);
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
         if (!METH) {
-            // 16 two-bit digits packed first-digit-most-significant: ((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes
+            // 16 two-bit digits packed first-digit-most-significant: ((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes.
+            // k-mers 2j, 2j+1 of the lane = the two k-mers of the (k+1)-mer at digit 2j: ONE 16-byte gather for both.
+            // The four pairs are visited in ROTATED order jj(j) = (j + lane/2) & 3 so that the 16-byte parameter stores
+            // of a quarter-warp fall into 8 different bank groups.
             const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
                                ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
-            const int sh0 = 32 - 2 * p.k;
+            const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
+            const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
+            const int rot = lane >> 1;
+            float4 mv[4];
 #pragma unroll
-            for (int j = 0; j < 8; j++) ranks[j] = (P >> (sh0 - 2 * ((j + rot) & 7))) & p.kmask;
+            for (int j = 0; j < 4; j++) {
+                uint32_t r = (P >> (sh0 - 4 * ((j + rot) & 3))) & pmask;
+                if (nk_tile < TK && m0 + 2 * ((j + rot) & 3) >= nk_tile) r = 0;
+                mv[j] = __ldg(&p.pair_model[r]);
+            }
+            if (m0 < nk_tile) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 pa = make_par(mv[j].x, mv[j].y), pb = make_par(mv[j].z, mv[j].w);
+                    *reinterpret_cast<float4 *>(smem + par_off + 8 * (m0 + 2 * ((j + rot) & 3))) = make_float4(pa.x, pa.y, pb.x, pb.y);
+                }
+            }
         } else {
             const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
             const int km1 = p.k - 1;
-            uint32_t rank = 0;
+            uint32_t rank = 0, ranks[8];
 #pragma unroll
             for (int i = 0; i < 8; i++)
                 if (i < km1) rank = rank * 5 + ((dw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
@@ -642,138 +804,84 @@ __device__ __forceinline__ TileHdr prepare_tile(const GenParams &p, const TileDe
                 const int bi = km1 + j;
                 const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
                 rank = (rank % p.kmask) * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);
-                ranks[j] = rank;
+                ranks[j] = (m0 + j < nk_tile) ? rank : 0u;
             }
-        }
-        if (nk_tile < TK) {
+            float2 mv[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (m0 + ((j + rot) & 7) >= nk_tile) ranks[j] = 0;
-        }
-    }
-    float2 mv[8];
+            for (int j = 0; j < 8; j++) mv[j] = __ldg(&p.model[ranks[j]]);
+            if (m0 < nk_tile) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) mv[j] = MODEL_SMEM ? model[ranks[j]] : __ldg(&model[ranks[j]]);
-
-    // (6) chunk -> k-mer map and boundary bitmap (needs only the dwells: runs while the gathers are in flight)
-    if (RAND_DWELL) {
-        static_assert(MAPC / 16 <= 96, "three 16-byte stores per lane must cover the boundary bitmap");
-#pragma unroll
-        for (int u = 0; u < 3; u++)
-            if (lane + 32 * u < MAPC / 16) sts_zero16(ws.bmap + 16 * (lane + 32 * u));
-        __syncwarp();
-        if (active) {
-            uint32_t pos = o + ph;  // the k-mer starts at bit (pos&7) of chunk (pos>>3)
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int m = m0 + j;
-                if (nk_tile == TK || m < nk_tile) {
-                    // chunks whose first (clipped) sample falls inside this k-mer get it as their first k-mer
-                    uint32_t w0 = (j == 0 && m0 == 0) ? 0u : (pos + 7) >> 3;
-                    const uint32_t end = pos + (uint32_t)d[j];
-                    const uint32_t w1 = (end + 7) >> 3;
-                    const uint32_t a = ws.map + w0;
-                    if (w0 < w1) sts_u8(a, (uint32_t)m);
-                    if (w0 + 1 < w1) sts_u8(a + 1, (uint32_t)m);
-                    if (w0 + 2 < w1) sts_u8(a + 2, (uint32_t)m);
-                    for (w0 += 3; w0 < w1; w0++) sts_u8(ws.map + w0, (uint32_t)m);
-                    if (!(j == 0 && m0 == 0)) atoms_or(ws.bmap + ((pos >> 3) & ~3u), 1u << (pos & 31));
-                    pos = end;
-                }
+                for (int j = 0; j < 8; j++) *reinterpret_cast<float2 *>(smem + par_off + 8 * (m0 + j)) = make_par(mv[j].x, mv[j].y);
             }
         }
     }
-    if (p.want_ss && active) {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (m0 + j < nk_tile) p.ss[td.ss_pos + m0 + j] = d[j];
-    }
-
-    // (7) per-k-mer parameters from the gathered (level_mean, level_stdv)
-    if (active) {
-        const float scale_f = (float)p.scale, off_f = (float)offset;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            float2 pr;
-            if (NOISY) {
-                // single precision, rounded once each: A' = (stdv*amp_noise)*scale, B' = fma(mean, scale, -offset)
-                pr = make_float2(__fmul_rn(__fmul_rn(mv[j].y, p.amp_noise), scale_f), fmaf(mv[j].x, scale_f, -off_f));
-            } else {
-                // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
-                const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), offset);
-                pr = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
-            }
-            sts_f2(ws.par + 8 * (m0 + ((j + rot) & 7)), pr);  // rows beyond the tile are never read
-        }
-    }
+    TileCtx h;
+    h.S = S; h.ph = ph;
+    h.C0 = REV ? ((L - B + ph) >> 3) - 1u : (B >> 3);
+    h.r_lo = td.r_lo; h.r_hi = td.r_hi;
+    h.out = p.sig + *reinterpret_cast<const int64_t *>(smem + sigoff_off);
     __syncwarp();
-    TileHdr h;
-    h.S = S; h.ph = ph; h.B = B; h.L = L; h.r_lo = key.r_lo; h.r_hi = key.r_hi;
-    h.out = p.sig + sigoff;
     return h;
 }
 
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool MODEL_SMEM>
-__global__ void __launch_bounds__(K4_MAX_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
-    constexpr bool USE_Z = NOISY || RAND_DWELL;
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
+__global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
+    constexpr bool USE_Z = NOISY;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
-    const int nw = blockDim.x >> 5;
     const int warp = tid >> 5, lane = tid & 31;
-    const K4Layout &lay = p.lay;
-    uint4 *lut = reinterpret_cast<uint4 *>(smem + lay.lut);
-    uint8_t *code = smem + lay.code;
-    unsigned long long *stage_bar = reinterpret_cast<unsigned long long *>(smem + lay.mbar);
-    __half *z16s = reinterpret_cast<__half *>(smem + lay.z16);
-    float2 *models = reinterpret_cast<float2 *>(smem + lay.model);
+    unsigned long long *stage_bar = reinterpret_cast<unsigned long long *>(smem + SM_MBAR);
+    const uint32_t par_off = SM_PAR + (uint32_t)warp * (TK * 8);
+    const uint32_t map_off = SM_WARP + (uint32_t)warp * WARP_BYTES;
+    const uint32_t wbase = opaque_smem_addr(smem + map_off);  // this warp's buffer, for the asynchronous copies
 
-    // ---- prologue: tables ----
+    // ---- prologue: tables; this warp's first descriptor ----
+    const int gwarp = blockIdx.x * K4_WARPS + warp;
+    const int stride = gridDim.x * K4_WARPS;
+    const bool has_work = gwarp < p.n_tiles;
+    if (has_work) {
+        fetch_tile_desc(p, wbase, W_DESC, gwarp, lane);
+        cp_async_commit();
+    }
+    if (smem_u32(smem) != SMEM_ORIGIN) __trap();  // lds_f32 & co. address shared memory absolutely (the host checks this too)
     if (tid == 0) mbar_init(stage_bar, 1);
-    for (int i = tid; i < 256; i += blockDim.x) code[i] = base_code(i);
-    for (int i = tid; i < 128 * LUT_COPIES; i += blockDim.x) {
-        const int m = (i / LUT_COPIES) << 1;  // boundary mask (bit 0 is never used)
-        uint32_t f[8], cnt = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (j >= 1 && ((m >> j) & 1)) cnt++;
-            f[j] = cnt * 8;
-        }
-        lut[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
-    }
+    for (int i = tid; i < 256; i += K4_THREADS) smem[SM_CODE + i] = base_code(i);
     __syncthreads();
-    if (tid == 0) {
-        uint32_t bytes = 0;
-        if (USE_Z) bytes += Z16_N * 2;
-        if (MODEL_SMEM) bytes += p.num_kmer * 8;
-        if (bytes) {
-            mbar_expect_tx(stage_bar, bytes);
-            if (USE_Z) {
-                tma_load_1d(z16s, p.z16, Z16_N, stage_bar);  // two 64 KB bulk copies
-                tma_load_1d(z16s + Z16_N / 2, p.z16 + Z16_N / 2, Z16_N, stage_bar);
-            }
-            if (MODEL_SMEM) tma_load_1d(models, p.model, p.num_kmer * 8, stage_bar);
+    if (USE_Z) {
+        if (tid == 0) {
+            mbar_expect_tx(stage_bar, Z32_BYTES);
+            tma_load_1d(smem + SM_Z, p.z32, Z32_BYTES / 2, stage_bar);  // two 64 KB bulk copies
+            tma_load_1d(smem + SM_Z + Z32_BYTES / 2, reinterpret_cast<const unsigned char *>(p.z32) + Z32_BYTES / 2, Z32_BYTES / 2, stage_bar);
         }
+        mbar_wait(stage_bar, 0);
     }
-    if (USE_Z || MODEL_SMEM) mbar_wait(stage_bar, 0);
-    float2 *par = reinterpret_cast<float2 *>(smem + lay.par) + warp * TK;
-    uint8_t *map = smem + lay.map + warp * MAPC;
-    uint8_t *bmap = smem + lay.bmap + warp * MAPC;
-    uint8_t *dig = smem + lay.digit + warp * DIG_BYTES;
-    if (smem_u32(par) + TK * 8 + 64 >= 0x10000u) __trap();
-    const float2 *__restrict__ model = MODEL_SMEM ? models : p.model;
-    const WarpSmem ws{smem_u32(par), smem_u32(map), smem_u32(bmap), smem_u32(dig), smem_u32(lut), smem_u32(z16s)};
+    if (!has_work) return;
+    cp_async_wait_all();
+    __syncwarp();
+    fetch_tile_inputs<RAND_DWELL>(p, smem, wbase, map_off, map_off + W_DESC, map_off + W_SIGOFF, gwarp, lane);
+    fetch_tile_desc(p, wbase, W_DESC + 80, min(gwarp + stride, p.n_tiles - 1), lane);
+    cp_async_commit();
 
-    // ---- main loop: this warp's tiles ----
-    const int gwarp = blockIdx.x * nw + warp;
-    const int stride = gridDim.x * nw;
-    if (gwarp >= p.n_tiles) return;
-    TileDesc td_next = load_tile_desc(p.tiles, gwarp);
+    // ---- main loop: this warp's tiles; the inputs of tile t+1 and the descriptor of tile t+2 fly during phase B of t ----
+    uint32_t slot = 0;
     for (int tile = gwarp; tile < p.n_tiles; tile += stride) {
-        const TileDesc td = td_next;
-        td_next = load_tile_desc(p.tiles, min(tile + stride, p.n_tiles - 1));  // in flight during this tile
-        const TileHdr h = prepare_tile<NOISY, RAND_DWELL, METH, REV, MODEL_SMEM>(p, td, lane, ws, dig, code, model);
-        emit_tile<NOISY, RAND_DWELL, REV>(p, ws, h, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        const uint32_t desc_off = map_off + W_DESC + slot * 80, sigoff_off = map_off + W_SIGOFF + slot * 8;
+        const TileCtx h = prepare_tile<NOISY, RAND_DWELL, METH, REV>(p, lane, smem, par_off, map_off, desc_off, sigoff_off);
+        const int next = tile + stride;
+        if (next < p.n_tiles) {
+            fetch_tile_inputs<RAND_DWELL>(p, smem, wbase, map_off, map_off + W_DESC + (slot ^ 1) * 80, map_off + W_SIGOFF + (slot ^ 1) * 8, next, lane);
+            fetch_tile_desc(p, wbase, W_DESC + slot * 80, min(next + stride, p.n_tiles - 1), lane);
+            cp_async_commit();
+        }
+#ifndef SQG_KO_PHASEB
+        emit_tile<NOISY, RAND_DWELL, REV>(p, smem, h, lane, par_off, map_off);
+#else
+        if (h.S == 0x7fffffffu) emit_tile<NOISY, RAND_DWELL, REV>(p, smem, h, lane, par_off, map_off);
+#endif
         __syncwarp();  // the tile buffer is rewritten by the next prepare_tile
+        slot ^= 1;
     }
 }
 

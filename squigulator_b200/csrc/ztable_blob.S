@@ -1,4 +1,4 @@
-/* Embeds data/ztable_v2.bin (Z1[32768] ++ Z2[16384], float32 LE; scripts/make_ztable.py) into libsqg.so */
+/* Embeds data/ztable_v3.bin (Z32[32768] ++ Z2[8192], float32 LE; scripts/make_ztable.py) into libsqg.so */
     .section .rodata
     .global sqg_ztable_blob
     .type   sqg_ztable_blob, @object

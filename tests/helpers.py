@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-ZTABLE = os.path.join(ROOT, "squigulator_b200", "data", "ztable_v2.bin")
+ZTABLE = os.path.join(ROOT, "squigulator_b200", "data", "ztable_v3.bin")
 
 PROFILE_FIELDS = ["digitisation", "sample_rate", "bps", "range", "offset_mean", "offset_std",
                   "median_before_mean", "median_before_std", "dwell_mean", "dwell_std"]
@@ -62,6 +62,11 @@ def load_oracle():
                                 C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int64)]
     lib.sqo_free_buf.argtypes = [C.c_void_p]
     lib.sqo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.sqo_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
+    lib.sqo_z32.restype = C.c_float
+    lib.sqo_z32.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.sqo_fma_rz.restype = C.c_float
+    lib.sqo_fma_rz.argtypes = [C.c_float, C.c_float, C.c_float]
     lib.sqo_kmer_rank.restype = C.c_uint32
     lib.sqo_kmer_rank.argtypes = [C.c_char_p, C.c_uint32]
     lib.sqo_meth_kmer_rank.restype = C.c_uint32
@@ -74,8 +79,8 @@ def load_oracle():
 
 
 def load_ztable():
-    t = np.fromfile(ZTABLE, dtype=np.uint8)  # Z16[65536] binary16 ++ Z2[16384] binary32
-    assert t.size == 65536 * 2 + 16384 * 4
+    t = np.fromfile(ZTABLE, dtype=np.uint8)  # Z32[32768] binary32 ++ Z2[8192] binary32
+    assert t.size == 32768 * 4 + 8192 * 4
     return np.ascontiguousarray(t)
 
 

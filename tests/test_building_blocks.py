@@ -23,10 +23,47 @@ def test_philox4x32_10_known_answers(oracle_lib):
         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
 
 
+def philox_r(lib, ctr, key, rounds):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib.sqo_philox4x32(c, k, rounds, o)
+    return list(o)
+
+
+def test_fma_rz_is_exact(oracle_lib):
+    """sqo_fma_rz == the exactly computed x*y+z rounded toward zero to binary32 (PTX fma.rz.f32)."""
+    from fractions import Fraction
+    import struct
+
+    def rz32(q):
+        if q == 0:
+            return 0.0
+        sgn, a = (-1 if q < 0 else 1), abs(q)
+        e = a.numerator.bit_length() - a.denominator.bit_length()
+        if Fraction(2) ** e > a:
+            e -= 1
+        e = max(e, -126)
+        m = int(a / Fraction(2) ** (e - 23))  # floor: toward zero
+        return sgn * float(Fraction(m) * Fraction(2) ** (e - 23))
+
+    rs = np.random.RandomState(5)
+    xs = rs.standard_normal(3000).astype(np.float32)
+    ys = (rs.uniform(0.5, 40, 3000)).astype(np.float32)
+    zs = (rs.uniform(32768, 36000, 3000)).astype(np.float32)
+    zs[::3] = (rs.uniform(-50, 2000, 1000)).astype(np.float32)
+    zs[5::7] = np.round(zs[5::7])            # integers: the sum lands just below/above an integer
+    xs[11::13] *= np.float32(1e-6)
+    for x, y, z in zip(xs, ys, zs):
+        want = rz32(Fraction(float(x)) * Fraction(float(y)) + Fraction(float(z)))
+        got = oracle_lib.sqo_fma_rz(float(x), float(y), float(z))
+        assert struct.pack("<f", got) == struct.pack("<f", want), (x, y, z)
+
+
 def test_philox_matches_independent_python(oracle_lib):
-    def ref(ctr, key):
+    def ref(ctr, key, rounds=10):
         c, k = list(ctr), list(key)
-        for _ in range(10):
+        for _ in range(rounds):
             p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
             c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
             k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
@@ -36,6 +73,7 @@ def test_philox_matches_independent_python(oracle_lib):
         ctr = [int(x) for x in rs.randint(0, 2 ** 32, 4, dtype=np.uint64)]
         key = [int(x) for x in rs.randint(0, 2 ** 32, 2, dtype=np.uint64)]
         assert philox(oracle_lib, ctr, key) == ref(ctr, key)
+        assert philox_r(oracle_lib, ctr, key, 7) == ref(ctr, key, 7)
 
 
 def test_lehmer_stream_is_minstd(oracle_lib):

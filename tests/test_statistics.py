@@ -91,9 +91,9 @@ def test_per_read_draws(oracle_lib, ztable):
     for x, m, s in ((offs, prof["offset_mean"], prof["offset_std"]), (meds, prof["median_before_mean"], prof["median_before_std"])):
         assert abs(x.mean() - m) < 4.5 * s / np.sqrt(n)
         assert abs(x.std() - s) < 4.5 * s / np.sqrt(2 * n)
-        # ~2^26 atoms (pairs of distinct binary16 table values): a handful of repeats among 20k reads at most; the
+        # ~2^40 atoms (four table normals per deviate): no repeats among 20k reads; the
         # reference's own smoke test looks for duplicates among 100 reads (scripts/test.sh:152-167)
-        assert len(np.unique(x)) >= n - 12 and len(np.unique(x[:100])) == 100
+        assert len(np.unique(x)) >= n - 1 and len(np.unique(x[:100])) == 100
     assert abs(np.corrcoef(offs, meds)[0, 1]) < 4.5 / np.sqrt(n)
 
 

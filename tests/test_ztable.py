@@ -1,40 +1,55 @@
-"""The quantile tables (squigulator_b200/data/ztable_v2.bin) re-derived independently (mpmath) + their invariants."""
+"""The quantile tables (squigulator_b200/data/ztable_v3.bin) re-derived independently (mpmath) + their invariants."""
 import numpy as np
 import pytest
 
 from tests import helpers as H
 
+N1 = 16384
+
+
+def fine_cell(m, c):
+    return 32 * m + (31 - c if m & 1 else c)
+
 
 @pytest.fixture(scope="module")
 def tables():
     raw = H.load_ztable()
-    z16 = raw[:65536 * 2].view("<f2").astype(np.float64)
-    z2 = raw[65536 * 2:].view("<f4").astype(np.float64)
-    return z16, z2
+    z32 = raw[:32768 * 4].view("<f4")
+    z2 = raw[32768 * 4:].view("<f4").astype(np.float64)
+    return z32, z2
 
 
 def test_layout_and_symmetry(tables):
-    z16, z2 = tables
-    assert z16.size == 65536 and z2.size == 2 * 8192
-    assert np.array_equal(z16[32768:], -z16[:32768])           # bit 15 of the index is the sign
-    assert np.all(np.diff(z16[:32768]) >= 0) and z16[0] > 0     # monotone half-normal quantiles
+    z32, z2 = tables
+    assert z32.size == 32768 and z2.size == 8192
+    bits = z32.view("<u4")
+    tail = (511 << 5) | 0
+    assert bits[tail] == 0x7FC00000 and bits[N1 + tail] == 0x7FC00000      # the two NaN sentinels ...
+    assert np.count_nonzero(np.isnan(z32)) == 2                             # ... and no other
+    ok = ~np.isnan(z32[:N1])
+    assert np.array_equal(z32[N1:][ok], -z32[:N1][ok])                      # bit 14 of the index is the sign
+    assert np.all(z32[:N1][ok] > 0)
+    for c in range(32):                                                      # every class: increasing with the slot m
+        v = z32[c:N1:32].astype(np.float64)
+        v = v[~np.isnan(v)]
+        assert np.all(np.diff(v) > 0)
     assert np.all(np.diff(z2) > 0)
-    assert float(z16[32766]) == 4.08203125                      # Z_TAIL_THR in sqg_device.cuh
-    assert abs(float(z2[-1]) - 6.0590086) < 1e-6                # Z_MAX in sqg_device.cuh
+    assert abs(float(z2[-1]) - 5.9104958) < 1e-6                            # Z_MAX in sqg_device.cuh
 
 
-def test_unit_variance(tables):
-    z16, z2 = tables
-    body = (z16[:32766] ** 2).sum() / 32768
-    tail = (z2 ** 2).sum() / (32768 * 8192)
-    assert abs(body + tail - 1.0) < 5e-6      # two-level law, incl. the fp16 rounding of the body
-    assert abs((z16[:32768] ** 2).mean() - 1.0) < 5e-6
+def test_every_class_has_mean_zero_and_unit_variance(tables):
+    z32, z2 = tables
+    for c in range(32):
+        v = z32[c:N1:32].astype(np.float64) ** 2
+        if c == 0:
+            v[511] = (z2 ** 2).mean()           # the refined tail cell
+        assert abs(v.mean() - 1.0) < 2e-7, c
 
 
 def test_cells_match_mpmath(tables):
     mp = pytest.importorskip("mpmath")
     mp.mp.dps = 30
-    z16, z2 = tables
+    z32, z2 = tables
 
     def edge(p):
         return mp.sqrt(2) * mp.erfinv(2 * mp.mpf(p) - 1)
@@ -44,30 +59,35 @@ def test_cells_match_mpmath(tables):
         den = mp.quad(lambda z: mp.npdf(z), [a, b])
         return float(mp.sqrt(num / den))
 
-    for i in (0, 7, 1000, 16384, 30000, 32765):
-        a = edge(mp.mpf(1) / 2 + mp.mpf(i) / 65536)
-        b = edge(mp.mpf(1) / 2 + mp.mpf(i + 1) / 65536)
-        r = rms(a, b)
-        assert abs(float(np.float16(r)) - z16[i]) <= abs(r) * 2 ** -10, i   # same value up to one fp16 ulp
-    for t, j in ((0, 0), (0, 4096), (1, 8190)):
-        i = 32766 + t
-        a = edge(mp.mpf(1) / 2 + (mp.mpf(i) + mp.mpf(j) / 8192) / 65536)
-        b = edge(mp.mpf(1) / 2 + (mp.mpf(i) + mp.mpf(j + 1) / 8192) / 65536)
-        assert abs(rms(a, b) - z2[t * 8192 + j]) < 1e-6
-    a = edge(mp.mpf(1) / 2 + (mp.mpf(32767) + mp.mpf(8191) / 8192) / 65536)
-    assert abs(rms(a, mp.inf) - z2[-1]) < 1e-6
+    def cell(f):
+        return rms(edge(mp.mpf(1) / 2 + mp.mpf(f) / 32768), edge(mp.mpf(1) / 2 + mp.mpf(f + 1) / 32768))
+
+    # the ratio table / conditional RMS is one constant per class (the unit-variance scale), within 0.7 % of 1
+    for c in (0, 5, 31):
+        ratios = []
+        for m in (0, 1, 100, 255, 400, 510):
+            ratios.append(float(z32[(m << 5) | c]) / cell(fine_cell(m, c)))
+        assert max(ratios) - min(ratios) < 3e-7, (c, ratios)
+        assert abs(ratios[0] - 1.0) < 7e-3
+        if c == 0:
+            s0 = ratios[0]
+    for j in (0, 4096, 8190):
+        a = edge(mp.mpf(1) / 2 + (mp.mpf(16383) + mp.mpf(j) / 8192) / 32768)
+        b = edge(mp.mpf(1) / 2 + (mp.mpf(16383) + mp.mpf(j + 1) / 8192) / 32768)
+        assert abs(s0 * rms(a, b) - z2[j]) < 2e-6
+    a = edge(mp.mpf(1) / 2 + (mp.mpf(16383) + mp.mpf(8191) / 8192) / 32768)
+    assert abs(s0 * rms(a, mp.inf) - z2[-1]) < 2e-6
 
 
-def test_bank_stratification_covers_the_table():
-    """stratify(): replacing bits 1-5 by the block number's low bits keeps 2^11 cells per block class, evenly spread,
-    and the 32 classes partition the table."""
-    h = np.arange(65536, dtype=np.uint32)
-    seen = np.zeros(65536, dtype=np.int32)
-    for block in range(32):
-        idx = np.unique((h & 0xFFC1) | ((block & 31) << 1))
-        assert idx.size == 2048
-        assert np.all(((idx >> 1) & 31) == block)          # all in shared-memory bank `block`
-        seen[idx] += 1
-        # evenly spread over the quantile range: one pair of adjacent cells in every run of 64 cells
-        assert np.array_equal(np.unique(idx >> 6), np.arange(1024))
+def test_classes_partition_the_cells():
+    """index = (r10 << 5) | class: a class owns 512 half-normal cells, one in every run of 32 fine cells, and the 32
+    classes partition the 16384 cells; the class is the shared-memory bank of the 4-byte entry."""
+    seen = np.zeros(N1, dtype=np.int32)
+    for c in range(32):
+        cells = np.array([fine_cell(m, c) for m in range(512)])
+        assert np.array_equal(cells >> 5, np.arange(512))
+        seen[cells] += 1
+        idx = (np.arange(512) << 5) | c
+        assert np.all((idx & 31) == c)
     assert np.all(seen == 1)
+    assert fine_cell(511, 0) == N1 - 1          # the refined cell is the outermost one
