@@ -43,7 +43,7 @@ extern "C" {
 #define SQG_PREFIX 0x020u     /* adaptor/stall (DNA) or polyA/adaptor/stall (RNA), src/genread.c:71-123 */
 
 /* Random-number schemes */
-#define SQG_RNG_PHILOX 0 /* counter-based Philox4x32-10; every draw addressed by (read, k-mer | sample);
+#define SQG_RNG_PHILOX 0 /* counter-based Philox4x32-7; every draw addressed by (read, k-mer | sample);
                             output independent of batching, threads and GPU count */
 #define SQG_RNG_LEGACY 1 /* the reference's minstd streams (src/rand.h, src/sim.c:215-258) reproduced by
                             jump-ahead: bit-compatible with `squigulator -t1` for the same read order */

@@ -390,8 +390,7 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
     tile_desc_kernel<<<(int)((s.n_segs + 255) / 256), 256, 0, s.stream>>>(p);
     ctx->launches++;
     const int g2 = (int)((s.n_reads + 255) / 256);
-    const int tiles_per_cta = K1_THREADS / 32;
-    const int g1 = (int)((s.n_tiles + tiles_per_cta - 1) / tiles_per_cta);
+    const int g1 = (int)((s.n_tiles + 3) / 4);  // legacy dwell kernel: 4 tiles (warps) per CTA
     if (ctx->legacy) {
         const LegacyParams q = legacy_params(ctx, s);
         legacy_dwell_kernel<<<g1, 128, 0, s.stream>>>(p, q);
@@ -400,7 +399,7 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
         ctx->launches += 3;
     } else {
         if (ctx->rand_dwell) {
-            dwell_kernel<<<g1, K1_THREADS, 0, s.stream>>>(p);
+            dwell_kernel<<<std::min<int>(ctx->num_sms, (int)((s.n_tiles + K1_THREADS / 32 - 1) / (K1_THREADS / 32))), K1_THREADS, K1_SMEM, s.stream>>>(p);
             ctx->launches++;
             read_plan_kernel<true><<<g2, 256, 0, s.stream>>>(p);
         } else {
@@ -701,6 +700,7 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
         ctx->base.wide = (finite && lo > -16000.0 && hi < 98000.0) ? 0 : 1;
     }
 
+    CU(cudaFuncSetAttribute((const void *)dwell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
     if (SM_TOTAL > prop.sharedMemPerBlockOptin) return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
     {

@@ -100,7 +100,6 @@ struct GenParams {
     int32_t shift_val;  // (int16)(30*digitisation/range)
 };
 
-constexpr int K1_THREADS = 128;  // 4 tiles per CTA, one warp each
 constexpr int TK = 256;          // k-mers per tile at most (32 lanes x 8); also the row length of GenParams::dwells
 
 // ------------------------------------------------------------------------------------------------
@@ -153,38 +152,60 @@ __global__ void __launch_bounds__(256) tile_desc_kernel(const __grid_constant__ 
     }
 }
 
-// K1: the dwells (random-dwell modes only; src/gensig.c:255-256).  One warp per tile, one lane per Philox block of 8
-// k-mers: 8 table normals -> 8 dwells, stored as one 16-byte row piece of uint16 (k-mers beyond the tile get 0), the
-// tile's sample count, and - when asked for - the reference's aln->ss (src/gensig.c:273-281).
-__global__ void __launch_bounds__(K1_THREADS) dwell_kernel(const __grid_constant__ GenParams p) {
-    const int tile = blockIdx.x * (K1_THREADS / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (tile >= p.n_tiles) return;
-    const TileDesc *td = p.tiles + tile;
-    const int nk_tile = td->nk;
-    const RngKey key{p.key0, p.key1, td->r_lo, td->r_hi};
-    uint32_t sum = 0;
-    uint32_t d[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) d[j] = 0;
-    if (lane * 8 < nk_tile) {
-        const uint32_t blk = (td->kidx0 >> 3) + lane;
-        const uint4 w = philox4x32_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
-        const int64_t ss0 = td->ss_pos + lane * 8;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float z = z_global(p.z32, p.z2, z_offset(draw_word(w, j), (blk & 31u) << 2), blk * 8 + j, key, ST_DWELL_TAIL);
-            if (lane * 8 + j < nk_tile) {
-                d[j] = (uint32_t)dwell_from_z(z, p.dwell_mean, p.dwell_std);
-                if (p.want_ss) p.ss[ss0 + j] = (int32_t)d[j];
-            }
-            sum += d[j];
-        }
+// K1: the dwells (random-dwell modes only; src/gensig.c:255-256).  Persistent CTAs (one per SM, 32 warps) with the
+// quantile table staged in shared memory by TMA; a warp takes a tile at a time, one lane per Philox block of 8 k-mers:
+// 8 table normals -> 8 dwells, stored as one 16-byte row piece of uint16 (k-mers beyond the tile get 0), the tile's
+// sample count, and - when asked for - the reference's aln->ss (src/gensig.c:273-281).
+constexpr int K1_THREADS = 1024;
+constexpr uint32_t K1_SMEM = Z32_BYTES + 16;
+__device__ __forceinline__ uint32_t smem_u32(const void *p);
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar);
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar, uint32_t count);
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, uint32_t bytes);
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t parity);
+
+__global__ void __launch_bounds__(K1_THREADS, 1) dwell_kernel(const __grid_constant__ GenParams p) {
+    extern __shared__ __align__(128) unsigned char smem1[];
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem1 + Z32_BYTES);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, Z32_BYTES);
+        tma_load_1d(smem1, p.z32, Z32_BYTES / 2, bar);
+        tma_load_1d(smem1 + Z32_BYTES / 2, reinterpret_cast<const unsigned char *>(p.z32) + Z32_BYTES / 2, Z32_BYTES / 2, bar);
     }
-    p.dwells[(size_t)tile * (TK / 8) + lane] = make_uint4(d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16));
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int lane = threadIdx.x & 31;
+    const int nw = K1_THREADS / 32;
+    for (int tile = blockIdx.x * nw + (threadIdx.x >> 5); tile < p.n_tiles; tile += gridDim.x * nw) {
+        const TileDesc *td = p.tiles + tile;
+        const int nk_tile = td->nk;
+        const RngKey key{p.key0, p.key1, td->r_lo, td->r_hi};
+        uint32_t sum = 0;
+        uint32_t d[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) p.tile_sum[tile] = sum;
+        for (int j = 0; j < 8; j++) d[j] = 0;
+        if (lane * 8 < nk_tile) {
+            const uint32_t blk = (td->kidx0 >> 3) + lane;
+            const uint4 w = philox4x32_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
+            const int64_t ss0 = td->ss_pos + lane * 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t off = z_offset(draw_word(w, j), (blk & 31u) << 2);
+                float z = *reinterpret_cast<const float *>(smem1 + off);
+                if (__builtin_expect(z_is_tail(off), 0)) z = z_tail(p.z2, off, blk * 8 + j, key, ST_DWELL_TAIL);
+                if (lane * 8 + j < nk_tile) {
+                    d[j] = (uint32_t)dwell_from_z(z, p.dwell_mean, p.dwell_std);
+                    if (p.want_ss) p.ss[ss0 + j] = (int32_t)d[j];
+                }
+                sum += d[j];
+            }
+        }
+        p.dwells[(size_t)tile * (TK / 8) + lane] = make_uint4(d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) p.tile_sum[tile] = sum;
+    }
 }
 
 // fixed-dwell modes with aln->ss requested: every k-mer has sps_fixed samples

@@ -102,6 +102,23 @@ def test_dwell_extremes(sq, oracle_lib, ztable):
     run_pair(sq, oracle_lib, ztable, H.PRESETS["dna-r10-min"][0], H.SQ_R10, 9, H.random_reads(6, 2500, seed=13), amp_noise=0.0)
 
 
+def test_sample_range_paths(sq, oracle_lib, ztable):
+    """The sample kernel reads the int16 out of the mantissa of fma.rz(z, A', B' + 32768) and sends everything outside
+    [0, 32768) - negative values, values that wrap around int16, tail cells of the table - through its exact path;
+    profiles it cannot bound at all run in `wide` mode.  All of them must equal the oracle bit for bit."""
+    reads = H.random_reads(8, 2500, seed=31)
+    base = dict(H.PRESETS["dna-r10-prom"][0])
+    neg = dict(base, offset_mean=1500.0)                      # every sample negative (truncation toward zero, not floor)
+    run_pair(sq, oracle_lib, ztable, neg, H.SQ_R10, 9, reads)
+    straddle = dict(base, offset_mean=700.0, offset_std=5.0)  # samples on both sides of zero inside one chunk
+    run_pair(sq, oracle_lib, ztable, straddle, H.SQ_R10, 9, reads)
+    big = dict(base, digitisation=65536.0, range=140.0)       # beyond int16: the reference's 16-bit wrap (wide mode)
+    run_pair(sq, oracle_lib, ztable, big, H.SQ_R10, 9, reads[:4])
+    run_pair(sq, oracle_lib, ztable, base, H.SQ_R10, 9, reads[:4], amp_noise=900.0)   # wide mode by the noise scale
+    edge = dict(base, digitisation=8192.0, range=30.0)        # values around 32768: fast path and exact path mixed
+    run_pair(sq, oracle_lib, ztable, edge, H.SQ_R10, 9, reads[:4])
+
+
 def test_batch_split_and_api_variants_agree(sq):
     """Output depends only on (seed, global read index, bases): not on batching, nor on which entry point is used."""
     reads = H.random_reads(24, 2500, seed=21, min_len=0)
