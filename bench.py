@@ -254,22 +254,28 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
         e_steps = max(6, min(steps, 24))
         checks = 0
 
-        def pipeline(n):
+        def pipeline(n, want=0):
             nonlocal checks
             inflight, tot, d2h = [], 0, 0
-            for i in range(n):
-                inflight.append(gen.submit(hb, e_off, first_read_index=first))
-                if len(inflight) == 3:
-                    t = inflight.pop(0)
-                    r = gen.wait(t)
-                    tot += r.total_samples
-                    d2h = int(r.sig_off[r.n_reads - 1] + ((r.len_raw_signal[r.n_reads - 1] + 63) & ~63)) * 2 + r.n_reads * 28
-                    checks ^= int(r.signal[0])  # touch the result on the host
-                    gen.release(t)
-            for t in inflight:
+
+            def finish(t):
+                nonlocal tot, d2h, checks
                 r = gen.wait(t)
                 tot += r.total_samples
+                if want & 2:   # SQG_WANT_SVB: svb-zd streams instead of raw int16
+                    d2h = int(r.svb_off[r.n_reads]) + r.n_reads * 44
+                    checks ^= int(r.svb[0])
+                else:
+                    d2h = int(r.sig_off[r.n_reads - 1] + ((r.len_raw_signal[r.n_reads - 1] + 63) & ~63)) * 2 + r.n_reads * 28
+                    checks ^= int(r.signal[0])  # touch the result on the host
                 gen.release(t)
+
+            for i in range(n):
+                inflight.append(gen.submit(hb, e_off, first_read_index=first, want=want))
+                if len(inflight) == 3:
+                    finish(inflight.pop(0))
+            for t in inflight:
+                finish(t)
             return tot, d2h
 
         pipeline(3)
@@ -282,6 +288,16 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
                       "h2d_bytes_per_step": nb + (e_reads * 64), "d2h_bytes_per_step": d2h,
                       "steps": e_steps, "reads_per_step_per_gpu": e_reads, "slots": 3,
                       "api": "sqg_submit/sqg_wait/sqg_release (pinned host bases in, pinned host int16 out)"}
+        # the same job with SQG_WANT_SVB: the signal crosses PCIe as slow5lib's svb-zd stream
+        pipeline(3, want=2)
+        barrier()
+        t0 = time.perf_counter()
+        tot, d2h = pipeline(e_steps, want=2)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out["e2e_svb"] = {"value": sum_over_ranks(float(tot)) / dt, "unit": "samples/s",
+                          "h2d_bytes_per_step": nb + (e_reads * 64), "d2h_bytes_per_step": d2h, "steps": e_steps,
+                          "api": "same call with SQG_WANT_SVB: svb-zd streams (zig-zag delta + StreamVByte, bit-identical to slow5lib's) out"}
         lib.sqg_host_free(hp)
     return out
 
@@ -378,7 +394,7 @@ def main():
                            "samples_per_step_per_gpu": res["samples_per_step_per_gpu"],
                            "l2": "output per step (GBs) far exceeds the 126 MB L2; no flush needed",
                            "rng": "philox4x32-7", "parallelism": f"reads sharded over {world} GPU(s), no hot-path collective"},
-                "clocks": res["clocks"], "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"],
+                "clocks": res["clocks"], "e2e": res.get("e2e"), "e2e_svb": res.get("e2e_svb"), "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "cpu_baseline": cpu, "store_only_gbs": res["store_only_gbs"],
                 "wall_s_timed_region": res["wall_s"], "other_workloads": extra}
         print(json.dumps(line), flush=True)

@@ -102,7 +102,11 @@ void sqg_host_free(void *p);
 
 /* ---- one batch of reads, host buffers in, host buffers out (replaces process_db's fan-out) ---- */
 
-#define SQG_WANT_SS 0x1u /* also return the per-k-mer dwell array (aln->ss, src/gensig.c:273-281) */
+#define SQG_WANT_SS 0x1u  /* also return the per-k-mer dwell array (aln->ss, src/gensig.c:273-281) */
+#define SQG_WANT_SVB 0x2u /* return every read's signal as slow5lib's svb-zd stream - exactly the bytes
+                             slow5_ptr_compress_solo(SLOW5_COMPRESS_SVB_ZD, raw_signal, ...) gives
+                             (slow5lib/src/slow5_press.c:1055-1087) - INSTEAD of raw int16: `signal` is NULL,
+                             `svb`/`svb_off` are set; ~1.3 bytes per sample cross PCIe instead of 2 */
 
 typedef struct {
     int64_t n_reads;
@@ -114,6 +118,9 @@ typedef struct {
     const double *median_before;   /* n_reads                         (src/gensig.c:317) */
     const int32_t *ss;             /* SQG_WANT_SS: dwell per k-mer, read i at ss[ss_off[i] .. ss_off[i+1]) */
     const int64_t *ss_off;         /* n_reads+1 */
+    const uint8_t *svb;            /* SQG_WANT_SVB: read i's stream = svb[svb_off[i] .. svb_off[i] + svb_len[i]) */
+    const int64_t *svb_off;        /* n_reads+1 (16-byte aligned starts; [n_reads] = bytes copied) */
+    const int64_t *svb_len;        /* n_reads */
 } sqg_result_t;
 
 /* bases: the reads' characters back to back (no terminators needed); read i = bases[base_off[i] ..

@@ -192,3 +192,15 @@ void sqref_close(void *hv) {
     free(core);
     free(h);
 }
+
+/* the reference's own signal compressor (slow5lib: zig-zag delta + StreamVByte), for pinning the svb-zd restatement.
+ * Returns the number of bytes written to out (<= cap), or -1. */
+#include <slow5/slow5_press.h>
+int64_t sqref_svb_zd(const int16_t *sig, int64_t n, uint8_t *out, int64_t cap) {
+    size_t bytes = 0;
+    void *p = slow5_ptr_compress_solo(SLOW5_COMPRESS_SVB_ZD, sig, (size_t)n * sizeof(int16_t), &bytes);
+    if (!p || (int64_t)bytes > cap) { free(p); return -1; }
+    memcpy(out, p, bytes);
+    free(p);
+    return (int64_t)bytes;
+}

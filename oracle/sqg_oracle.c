@@ -463,3 +463,29 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
     free(joined);
     return total;
 }
+
+/* ------------------------------------------------------------------ svb-zd */
+
+/* slow5lib's signal compression for BLOW5 records, restated: ptr_compress_svb_zd
+ * (slow5lib/src/slow5_press.c:1055-1087) = zig-zag delta with prev = 0
+ * (thirdparty/streamvbyte/src/streamvbyte_zigzag.c:15-27) then ptr_compress_svb (:1029-1052): a uint32
+ * sample count followed by the StreamVByte stream - ceil(n/4) key bytes holding 2 bits per value
+ * (bytes - 1, first value in the low bits), then the values little-endian in 1-4 bytes each
+ * (streamvbyte_encode.c:31-79).  out needs 4 + (n+3)/4 + 4n bytes.  Returns the bytes written. */
+int64_t sqo_svb_zd_encode(const int16_t *sig, int64_t n, uint8_t *out) {
+    uint32_t length = (uint32_t)n;
+    memcpy(out, &length, 4);
+    uint8_t *key = out + 4;
+    uint8_t *data = key + (n + 3) / 4;
+    int32_t prev = 0;
+    for (int64_t i = 0; i < n; i++) {
+        int32_t d = (int32_t)sig[i] - prev;
+        prev = sig[i];
+        uint32_t v = ((uint32_t)d + (uint32_t)d) ^ (uint32_t)(d >> 31);
+        uint32_t code = v < (1u << 8) ? 0 : v < (1u << 16) ? 1 : v < (1u << 24) ? 2 : 3;
+        if ((i & 3) == 0) key[i >> 2] = 0;
+        key[i >> 2] |= (uint8_t)(code << (2 * (i & 3)));
+        for (uint32_t b = 0; b <= code; b++) *data++ = (uint8_t)(v >> (8 * b));
+    }
+    return (int64_t)(data - out);
+}

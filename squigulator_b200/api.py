@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SQ_RNA, SQ_FULL_CONTIG, SQ_IDEAL, SQ_IDEAL_TIME, SQ_IDEAL_AMP, SQ_PREFIX, SQ_R10 = 0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040
 RNG_PHILOX, RNG_LEGACY = 0, 1
 WANT_SS = 0x1
+WANT_SVB = 0x2
 
 PROFILE_FIELDS = ("digitisation", "sample_rate", "bps", "range", "offset_mean", "offset_std",
                   "median_before_mean", "median_before_std", "dwell_mean", "dwell_std")
@@ -55,7 +56,8 @@ class Result(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("total_samples", C.c_int64), ("signal", C.POINTER(C.c_int16)),
                 ("sig_off", C.POINTER(C.c_int64)), ("len_raw_signal", C.POINTER(C.c_int64)),
                 ("offset", C.POINTER(C.c_double)), ("median_before", C.POINTER(C.c_double)),
-                ("ss", C.POINTER(C.c_int32)), ("ss_off", C.POINTER(C.c_int64))]
+                ("ss", C.POINTER(C.c_int32)), ("ss_off", C.POINTER(C.c_int64)),
+                ("svb", C.POINTER(C.c_uint8)), ("svb_off", C.POINTER(C.c_int64)), ("svb_len", C.POINTER(C.c_int64))]
 
 
 class SqgError(RuntimeError):
@@ -160,24 +162,32 @@ class SignalGenerator:
         o = np.ctypeslib.as_array(res.offset, shape=(n,))
         mb = np.ctypeslib.as_array(res.median_before, shape=(n,))
         span = int((off + ln).max())
-        sig = np.ctypeslib.as_array(res.signal, shape=(max(span, 1),))
+        sig = np.ctypeslib.as_array(res.signal, shape=(max(span, 1),)) if res.signal else None
         so = np.ctypeslib.as_array(res.ss_off, shape=(n + 1,))
         ss = np.ctypeslib.as_array(res.ss, shape=(max(int(so[-1]), 1),)) if res.ss else None
+        if res.svb:  # SQG_WANT_SVB: every read's signal as slow5lib's svb-zd stream instead of raw int16
+            vo = np.ctypeslib.as_array(res.svb_off, shape=(n + 1,))
+            vl = np.ctypeslib.as_array(res.svb_len, shape=(n,))
+            svb = np.ctypeslib.as_array(res.svb, shape=(max(int(vo[-1]), 1),))
         out = []
         for i in range(n):
-            s = sig[off[i]:off[i] + ln[i]]
-            d = dict(offset=float(o[i]), median_before=float(mb[i]), sig=s.copy() if copy else s)
+            d = dict(offset=float(o[i]), median_before=float(mb[i]), n_samples=int(ln[i]))
+            if sig is not None:
+                s = sig[off[i]:off[i] + ln[i]]
+                d["sig"] = s.copy() if copy else s
+            if res.svb:
+                d["svb"] = svb[vo[i]:vo[i] + vl[i]].copy()
             if ss is not None:
                 d["ss"] = ss[so[i]:so[i + 1]].copy()
             out.append(d)
         return out
 
     # -- the batch call (process_db's fan-out, reference src/sim.c:622)
-    def gen_batch(self, reads, first_read_index=0, want_ss=False):
+    def gen_batch(self, reads, first_read_index=0, want_ss=False, want_svb=False):
         bases, off = _pack_reads(reads)
         res = Result()
         self._check(self.lib.sqg_gen_batch(self.h, len(reads), bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
-                                           first_read_index, WANT_SS if want_ss else 0, C.byref(res)))
+                                           first_read_index, (WANT_SS if want_ss else 0) | (WANT_SVB if want_svb else 0), C.byref(res)))
         return self._unpack(res)
 
     def gen_batch_raw(self, bases, off, first_read_index=0, want=0):

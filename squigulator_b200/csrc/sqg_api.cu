@@ -27,6 +27,7 @@
 
 #include "sqg_kernels.cuh"
 #include "sqg_legacy.cuh"
+#include "sqg_svb.cuh"
 
 extern "C" const unsigned char sqg_ztable_blob[];  // Z32 ++ Z2 (binary32), embedded from data/ztable_v3.bin (ztable_blob.S)
 
@@ -109,6 +110,11 @@ struct Slot {
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
     DevBuf<int32_t> d_ss;
+    DevBuf<int64_t> d_svb_len, d_svb_off;   // SQG_WANT_SVB
+    DevBuf<uint8_t> d_svb;
+    PinBuf<int64_t> h_svb_len, h_svb_off;
+    PinBuf<uint8_t> h_svb;
+    int64_t svb_bytes = 0;
     // SQG_RNG_LEGACY scratch (per k-mer of the batch)
     DevBuf<uint32_t> d_rank, d_rank_sorted, d_idx, d_idx_sorted;
     DevBuf<uint64_t> d_dsorted, d_excl, d_heads, d_segstart, d_cpos;
@@ -134,6 +140,7 @@ struct Slot {
         h_segs.release(); h_reads.release(); h_meta.release(); h_sigoff.release(); h_len64.release();
         h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
         h_ss.release();
+        d_svb_len.release(); d_svb_off.release(); d_svb.release(); h_svb_len.release(); h_svb_off.release(); h_svb.release();
         for (auto e : kev) cudaEventDestroy(e);
         kev.clear();
         if (ev0) cudaEventDestroy(ev0);
@@ -387,9 +394,9 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
     if (s.n_reads == 0) return SQG_OK;
     const GenParams p = slot_params(ctx, s);
     CU(cudaMemsetAsync(s.d_meta.p, 0, 4 * sizeof(int64_t), s.stream));
-    tile_desc_kernel<<<(int)((s.n_segs + 255) / 256), 256, 0, s.stream>>>(p);
+    tile_desc_kernel<<<(int)((s.n_segs + 7) / 8), 256, 0, s.stream>>>(p);
     ctx->launches++;
-    const int g2 = (int)((s.n_reads + 255) / 256);
+    const int g2 = (int)((s.n_reads + 7) / 8);  // one warp per read
     const int g1 = (int)((s.n_tiles + 3) / 4);  // legacy dwell kernel: 4 tiles (warps) per CTA
     if (ctx->legacy) {
         const LegacyParams q = legacy_params(ctx, s);
@@ -497,9 +504,46 @@ int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent
     return SQG_OK;
 }
 
+// SQG_WANT_SVB: svb-zd streams of the batch's reads, in HBM (sqg_svb.cuh).  One small D2H + sync to size the buffer.
+int slot_compress(sqg_ctx *ctx, Slot &s) {
+    s.svb_bytes = 0;
+    if (s.n_reads == 0) return SQG_OK;
+    const size_t n = (size_t)s.n_reads;
+    CU(s.d_svb_len.ensure(n, false, s.stream));
+    CU(s.d_svb_off.ensure(n + 1, false, s.stream));
+    CU(s.h_svb_off.ensure(n + 1));
+    SvbParams q;
+    q.sig = s.d_sig.p; q.read_sigoff = s.d_sigoff.p; q.read_siglen = s.d_siglen.p;
+    q.svb_len = s.d_svb_len.p; q.svb_off = s.d_svb_off.p; q.svb = nullptr; q.n_reads = (int32_t)s.n_reads;
+    svb_size_kernel<<<(int)s.n_reads, SVB_THREADS, 0, s.stream>>>(q);
+    svb_offsets_kernel<<<1, 1024, 0, s.stream>>>(q);
+    CU(cudaMemcpyAsync(s.h_svb_off.p + n, s.d_svb_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    s.svb_bytes = s.h_svb_off.p[n];
+    CU(s.d_svb.ensure((size_t)std::max<int64_t>(s.svb_bytes, 16), false, s.stream));
+    q.svb = s.d_svb.p;
+    svb_encode_kernel<<<(int)s.n_reads, SVB_THREADS, 0, s.stream>>>(q);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return SQG_OK;
+}
+
 // D2H of everything the caller gets back; fills *res.  Synchronises the slot's stream.
 int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     const size_t n = (size_t)s.n_reads;
+    const bool svb = (s.want & SQG_WANT_SVB) != 0;
+    if (svb) {
+        CU(s.h_svb_len.ensure(n + 1));
+        CU(s.h_svb_off.ensure(n + 1));
+        CU(s.h_svb.ensure((size_t)std::max<int64_t>(s.svb_bytes, 16)));
+        if (n) {
+            CU(cudaMemcpyAsync(s.h_svb.p, s.d_svb.p, (size_t)s.svb_bytes, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_svb_len.p, s.d_svb_len.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_svb_off.p, s.d_svb_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            s.h_svb_off.p[0] = 0;
+        }
+    }
     CU(s.h_siglen.ensure(n + 1));
     CU(s.h_sigoff.ensure(n + 1));
     CU(s.h_len64.ensure(n + 1));
@@ -507,7 +551,7 @@ int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     CU(s.h_median.ensure(n + 1));
     CU(s.h_sig.ensure((size_t)std::max<int64_t>(s.arena_need, 64)));
     if (n) {
-        CU(cudaMemcpyAsync(s.h_sig.p, s.d_sig.p, (size_t)s.arena_need * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));
+        if (!svb) CU(cudaMemcpyAsync(s.h_sig.p, s.d_sig.p, (size_t)s.arena_need * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_siglen.p, s.d_siglen.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_sigoff.p, s.d_sigoff.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_offset.p, s.d_offset.p, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -522,13 +566,16 @@ int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     if (res) {
         res->n_reads = s.n_reads;
         res->total_samples = s.total_samples;
-        res->signal = s.h_sig.p;
+        res->signal = svb ? nullptr : s.h_sig.p;
         res->sig_off = s.h_sigoff.p;
         res->len_raw_signal = s.h_len64.p;
         res->offset = s.h_offset.p;
         res->median_before = s.h_median.p;
         res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
         res->ss_off = s.h_ss_off.p;
+        res->svb = svb ? s.h_svb.p : nullptr;
+        res->svb_off = svb ? s.h_svb_off.p : nullptr;
+        res->svb_len = svb ? s.h_svb_len.p : nullptr;
     }
     return SQG_OK;
 }
@@ -540,6 +587,7 @@ int slot_run_all(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
     if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
     if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
+    if ((want & SQG_WANT_SVB) && (rc = slot_compress(ctx, s)) != SQG_OK) return rc;
     return slot_fetch(ctx, s, res);
 }
 
@@ -841,13 +889,17 @@ int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res) {
         Slot &s = ctx->slots[job->slot];
         res->n_reads = s.n_reads;
         res->total_samples = s.total_samples;
-        res->signal = s.h_sig.p;
+        const bool svb = (s.want & SQG_WANT_SVB) != 0;
+        res->signal = svb ? nullptr : s.h_sig.p;
         res->sig_off = s.h_sigoff.p;
         res->len_raw_signal = s.h_len64.p;
         res->offset = s.h_offset.p;
         res->median_before = s.h_median.p;
         res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
         res->ss_off = s.h_ss_off.p;
+        res->svb = svb ? s.h_svb.p : nullptr;
+        res->svb_off = svb ? s.h_svb_off.p : nullptr;
+        res->svb_len = svb ? s.h_svb_len.p : nullptr;
     }
     return SQG_OK;
 }
@@ -962,6 +1014,10 @@ int sqg_dev_batch_fetch(sqg_ctx_t *ctx, sqg_dev_batch_t *b, sqg_result_t *res) {
     if (!ctx || !b || !res) return SQG_ERR_ARG;
     if (!b->planned) return fail(ctx, SQG_ERR_STATE, "batch has not been run");
     CU(cudaSetDevice(ctx->device));
+    if (b->slot.want & SQG_WANT_SVB) {
+        int rc = slot_compress(ctx, b->slot);
+        if (rc != SQG_OK) return rc;
+    }
     return slot_fetch(ctx, b->slot, res);
 }
 

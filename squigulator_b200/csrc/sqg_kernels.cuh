@@ -127,15 +127,16 @@ __global__ void __launch_bounds__(256) pair_model_kernel(const float2 *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: tile descriptors (one thread per segment)
+// K0: tile descriptors (one warp per segment, one lane per tile)
 __global__ void __launch_bounds__(256) tile_desc_kernel(const __grid_constant__ GenParams p) {
-    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    const int si = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (si >= p.n_segs) return;
     const SegDesc seg = p.segs[si];
     const int64_t ss0 = p.reads[seg.read].ss_off + seg.k0;
     const RngKey key = make_key(p, seg.read);
     const int nt = (seg.nk + p.T - 1) / p.T;
-    for (int t = 0; t < nt; t++) {
+    for (int t = lane; t < nt; t += 32) {
         const int kstart = t * p.T;
         TileDesc d;
         d.a_off = seg.off_a + kstart;
@@ -215,10 +216,12 @@ __global__ void __launch_bounds__(256) fixed_ss_kernel(const __grid_constant__ G
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: per read — scan its tiles, draw offset / median_before (src/gensig.c:312-318), complete the tile descriptors
+// K2: per read (one warp, one lane per tile) — scan its tiles, draw offset / median_before (src/gensig.c:312-318),
+// complete the tile descriptors
 template <bool RAND_DWELL>
 __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ GenParams p) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (r >= p.n_reads) return;
     const ReadDesc rd = p.reads[r];
     uint64_t total = 0;
@@ -226,28 +229,36 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
     for (int s = rd.seg0; s < rd.seg0 + rd.nseg; s++) {
         const SegDesc seg = p.segs[s];
         const int ntile = (seg.nk + p.T - 1) / p.T;
-        for (int t = 0; t < ntile; t++) {
+        for (int t0 = 0; t0 < ntile; t0 += 32) {
+            const int t = t0 + lane;
             const int tile = seg.tile0 + t;
-            uint32_t sum;
-            if (RAND_DWELL) {
-                sum = p.tile_sum[tile];
-            } else {
-                sum = (uint32_t)min(p.T, seg.nk - t * p.T) * (uint32_t)p.sps_fixed;
-                p.tile_sum[tile] = sum;
+            uint32_t sum = 0;
+            if (t < ntile) {
+                if (RAND_DWELL) {
+                    sum = p.tile_sum[tile];
+                } else {
+                    sum = (uint32_t)min(p.T, seg.nk - t * p.T) * (uint32_t)p.sps_fixed;
+                    p.tile_sum[tile] = sum;
+                }
             }
-            p.tiles[tile].B = (uint32_t)total;
-            p.tiles[tile].S = sum;
-            total += sum;
+            uint64_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (t < ntile) {
+                p.tiles[tile].B = (uint32_t)(total + inc - sum);
+                p.tiles[tile].S = sum;
+            }
+            total += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (s == rd.seg0) n0 = (uint32_t)total;
     }
     if (total >= 0xFFFFFFFFull) {  // src/sim.c:559-562
-        atomicExch((unsigned long long *)&p.meta[2], 1ull);
+        if (lane == 0) atomicExch((unsigned long long *)&p.meta[2], 1ull);
         total = 0;
     }
-    p.read_siglen[r] = (uint32_t)total;
-    p.read_n0[r] = n0;
-
     double off = p.offset_mean, med = p.median_mean;
     if (!p.ideal) {
         // one Philox block per read: draws 0-3 -> offset, 4-7 -> median_before, each a unit-norm mix of four table
@@ -270,12 +281,16 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
         off = __dadd_rn(__dmul_rn(z[0], p.offset_std), p.offset_mean);
         med = __dadd_rn(__dmul_rn(z[1], p.median_std), p.median_mean);
     }
-    p.read_offset[r] = off;
-    p.read_median[r] = med;
+    if (lane == 0) {
+        p.read_siglen[r] = (uint32_t)total;
+        p.read_n0[r] = n0;
+        p.read_offset[r] = off;
+        p.read_median[r] = med;
+    }
     for (int s = rd.seg0; s < rd.seg0 + rd.nseg; s++) {
         const SegDesc seg = p.segs[s];
         const int ntile = (seg.nk + p.T - 1) / p.T;
-        for (int t = 0; t < ntile; t++) {
+        for (int t = lane; t < ntile; t += 32) {
             TileDesc *td = p.tiles + seg.tile0 + t;
             td->offset = off;
             td->L = (uint32_t)total;

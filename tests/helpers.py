@@ -67,6 +67,8 @@ def load_oracle():
     lib.sqo_z32.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.sqo_fma_rz.restype = C.c_float
     lib.sqo_fma_rz.argtypes = [C.c_float, C.c_float, C.c_float]
+    lib.sqo_svb_zd_encode.restype = C.c_int64
+    lib.sqo_svb_zd_encode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.sqo_kmer_rank.restype = C.c_uint32
     lib.sqo_kmer_rank.argtypes = [C.c_char_p, C.c_uint32]
     lib.sqo_meth_kmer_rank.restype = C.c_uint32
@@ -183,3 +185,28 @@ def random_reads(n, mean_len, seed=3, alphabet=b"ACGT", min_len=1):
     lens = np.maximum(min_len, rs.gamma(2.0, mean_len / 2.0, n).astype(np.int64))
     al = np.frombuffer(alphabet, dtype=np.uint8)
     return [al[rs.randint(0, len(al), l)].tobytes() for l in lens]
+
+
+def oracle_svb_zd(lib, sig):
+    """slow5lib's svb-zd stream of one int16 signal, by the oracle's restatement"""
+    sig = np.ascontiguousarray(sig, dtype=np.int16)
+    out = np.empty(4 + (sig.size + 3) // 4 + 4 * sig.size + 16, dtype=np.uint8)
+    n = lib.sqo_svb_zd_encode(sig.ctypes.data_as(C.c_void_p), sig.size, out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()
+
+
+def svb_zd_decode(buf):
+    """independent decoder (numpy): the inverse of slow5lib's svb-zd, for round-trip properties"""
+    buf = np.asarray(buf, dtype=np.uint8)
+    n = int(buf[:4].view("<u4")[0])
+    keys = buf[4:4 + (n + 3) // 4]
+    codes = ((keys[:, None] >> (2 * np.arange(4))) & 3).reshape(-1)[:n].astype(np.int64)
+    nb = codes + 1
+    start = np.concatenate([[0], np.cumsum(nb)[:-1]]) + 4 + (n + 3) // 4
+    v = np.zeros(n, dtype=np.uint64)
+    for b in range(4):
+        sel = nb > b
+        v[sel] |= buf[start[sel] + b].astype(np.uint64) << np.uint64(8 * b)
+    v = v.astype(np.int64)
+    d = (v >> 1) ^ -(v & 1)
+    return np.cumsum(d).astype(np.int16), int(start[-1] + nb[-1]) if n else 4

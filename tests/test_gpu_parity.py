@@ -119,6 +119,31 @@ def test_sample_range_paths(sq, oracle_lib, ztable):
     run_pair(sq, oracle_lib, ztable, edge, H.SQ_R10, 9, reads[:4])
 
 
+def test_svb_zd_streams(sq, oracle_lib):
+    """SQG_WANT_SVB: the GPU's svb-zd stream of every read == the oracle's restatement of slow5lib's encoder run on the
+    raw signal of the same read (which tests/test_svb_zd.py pins to the compiled slow5lib), and decodes back to it."""
+    reads = H.random_reads(30, 2500, seed=41, min_len=0) + [b"", b"A", b"ACGTACGTAC"]
+    model = H.random_model(4 ** 9)
+    for prof, kw in (("dna-r10-prom", {}), ("dna-r10-prom", dict(flags=H.SQ_IDEAL_AMP)), ("rna004-prom", {})):
+        gen = sq.SignalGenerator(prof, model, 9, seed=3, **kw)
+        raw = gen.gen_batch(reads, first_read_index=50)
+        svb = gen.gen_batch(reads, first_read_index=50, want_svb=True, want_ss=True)
+        gen.close()
+        for a, b in zip(raw, svb):
+            assert "sig" not in b and b["n_samples"] == len(a["sig"])
+            want = H.oracle_svb_zd(oracle_lib, a["sig"])
+            assert np.array_equal(b["svb"], want), (len(a["sig"]), b["svb"][:12], want[:12])
+            dec, used = H.svb_zd_decode(b["svb"])
+            assert used == len(b["svb"]) and np.array_equal(dec, a["sig"])
+    # extreme deltas (3-byte codes): the wrap-around profile of test_sample_range_paths
+    big = dict(H.PRESETS["dna-r10-prom"][0], digitisation=65536.0, range=140.0)
+    gen = sq.SignalGenerator(big, model, 9, flags=H.SQ_R10, seed=3)
+    raw = gen.gen_batch(reads[:6]); svb = gen.gen_batch(reads[:6], want_svb=True)
+    gen.close()
+    for a, b in zip(raw, svb):
+        assert np.array_equal(b["svb"], H.oracle_svb_zd(oracle_lib, a["sig"]))
+
+
 def test_batch_split_and_api_variants_agree(sq):
     """Output depends only on (seed, global read index, bases): not on batching, nor on which entry point is used."""
     reads = H.random_reads(24, 2500, seed=21, min_len=0)
