@@ -371,9 +371,9 @@ constexpr int K4_THREADS = K4_WARPS * 32;  // register budget: 65536 / 512 = 128
 constexpr int MAPC = 1344;   // 8-sample chunks per tile: >= (TK*max_dwell + 14)/8 (dna-r10: 256 k-mers x 37)
 constexpr int DIG_BYTES = TK + 32;   // digits of the tile's base window; the same size holds the raw window (16-byte granules)
 // per-warp buffer
-constexpr uint32_t W_MAP = 0;                        // chunk -> k-mer of its first sample (u8)
-constexpr uint32_t W_BMAP = W_MAP + MAPC;            // chunk -> bit j: a k-mer starts at its sample j
-constexpr uint32_t W_DIG = W_BMAP + MAPC;            // base digits
+constexpr uint32_t W_MAP = 0;                        // per 32 samples (4 chunks) an 8-byte entry: {bit s = a k-mer (other than the
+                                                     // tile's first) starts at sample s, number of such starts before the entry}
+constexpr uint32_t W_DIG = W_MAP + 2 * MAPC;         // base digits
 constexpr uint32_t W_RAW = W_DIG + DIG_BYTES;        // prefetched base window (ASCII), 16-byte granules
 constexpr uint32_t W_DWELL = W_RAW + DIG_BYTES;      // prefetched dwells of the tile: TK x uint16
 constexpr uint32_t W_DESC = W_DWELL + TK * 2;        // two TileDesc slots
@@ -455,10 +455,15 @@ __device__ __forceinline__ float2 lds_f2(uint32_t off) {
     return v;
 }
 template <uint32_t IMM>
-__device__ __forceinline__ uint32_t lds_u8(uint32_t off) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+__device__ __forceinline__ uint2 lds_u2(uint32_t off) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
     return v;
+}
+// k-mer of a chunk's first sample and the chunk's boundary mask from its map entry (chunk w = byte w & 3 of the entry)
+__device__ __forceinline__ void entry_kmers(uint2 ent, uint32_t sh /* 8 * (w & 3) */, uint32_t &k0, uint32_t &m1) {
+    k0 = ent.y + __popc(ent.x & ((2u << sh) - 1u));   // starts at or before the chunk's first sample
+    m1 = (ent.x >> sh) & 0xFEu;                        // (a start on the chunk's first sample is not a boundary to cross)
 }
 
 // What phase B needs to know about the tile (registers, warp-uniform)
@@ -477,8 +482,7 @@ template <bool RAND_DWELL>
 __device__ __forceinline__ void chunk_kmers(const GenParams &p, const unsigned char *smem, uint32_t map_off, const TileCtx &t, uint32_t w,
                                             uint32_t &k0, uint32_t &m1) {
     if (RAND_DWELL) {
-        k0 = smem[map_off + W_MAP + w];
-        m1 = smem[map_off + W_BMAP + w] & 0xFEu;  // (a start on the chunk's first sample is not a boundary to cross)
+        entry_kmers(*reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * (w >> 2)), 8 * (w & 3), k0, m1);
     } else {
         const int s0 = (int)(8 * w) - (int)t.ph;
         k0 = div_sps(p, (uint32_t)max(s0, 0));
@@ -545,17 +549,20 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned cha
     // Software pipeline, one chunk deep: the Philox block and the map bytes of the lane's NEXT chunk are produced while
     // the table lookups and FFMAs of the current one are in flight (two independent dependency chains per warp).
     uint4 r4n = make_uint4(0, 0, 0, 0);
-    uint32_t k0n = 0, m1n = 0;
+    uint2 entn = make_uint2(0, 0);
+    const uint32_t ent_sh = 8 * (lane & 3);                       // w = lane (mod 32): the chunk's byte within its map entry
+    const uint32_t ent_lane = map_off + 8 * ((uint32_t)lane >> 2);
     {
         const uint32_t w = lane;
         if (NOISY) r4n = philox4x32_rk(REV ? t.C0 - w : t.C0 + w, t.r_lo, t.r_hi, ST_AMP, p.rk);
-        if (RAND_DWELL) { k0n = lds_u8<W_MAP>(map_off + w); m1n = lds_u8<W_BMAP>(map_off + w); }
+        if (RAND_DWELL) entn = lds_u2<W_MAP>(ent_lane);
     }
     for (uint32_t wb = 0; wb < nW; wb += 32) {   // wb is warp-uniform: 32 consecutive chunks per iteration
         const uint32_t w = wb + lane;
         if (w >= nW) break;
         const uint4 r4 = r4n;
-        uint32_t k0 = k0n, m1 = m1n & 0xFEu;  // (a start on the chunk's first sample is not a boundary to cross)
+        uint32_t k0 = 0, m1 = 0;
+        if (RAND_DWELL) entry_kmers(entn, ent_sh, k0, m1);
         {
             const uint32_t wn = w + 32;  // (past the tile's end for the last one: computed, never used)
 #ifdef SQG_KO_PHILOX
@@ -563,7 +570,7 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned cha
 #else
             if (NOISY) r4n = philox4x32_rk(REV ? t.C0 - wn : t.C0 + wn, t.r_lo, t.r_hi, ST_AMP, p.rk);
 #endif
-            if (RAND_DWELL) { k0n = lds_u8<W_MAP>(map_off + wn); m1n = lds_u8<W_BMAP>(map_off + wn); }
+            if (RAND_DWELL) entn = lds_u2<W_MAP>(ent_lane + 2 * wb + 64);   // entry of chunk wn = 8 * (wn >> 2)
         }
         if (!RAND_DWELL) chunk_kmers<RAND_DWELL>(p, smem, map_off, t, w, k0, m1);
         const uint32_t par0 = k0 * 8 + par_off;
@@ -729,11 +736,10 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
 
     // (2) warp scan of the dwells, then the chunk -> k-mer map and the boundary bitmap
     if (RAND_DWELL) {
-        static_assert(MAPC / 16 <= 96, "three 16-byte stores per lane must cover the boundary bitmap");
         const uint4 dq = *reinterpret_cast<const uint4 *>(smem + map_off + W_DWELL + lane * 16);
-#pragma unroll
-        for (int u = 0; u < 3; u++)
-            if (lane + 32 * u < MAPC / 16) *reinterpret_cast<uint4 *>(smem + map_off + W_BMAP + 16 * (lane + 32 * u)) = make_uint4(0, 0, 0, 0);
+        // clear the map entries this tile touches (+ the one-ahead read of the sample loop)
+        const uint32_t n_ent = min((((S + ph + 7) >> 3) + 3) / 4 + 9u, (uint32_t)(MAPC / 4));
+        for (uint32_t e = lane * 2; e < n_ent; e += 64) *reinterpret_cast<uint4 *>(smem + map_off + W_MAP + 8 * e) = make_uint4(0, 0, 0, 0);
         const uint32_t t4 = dq.x + dq.y + dq.z + dq.w;  // packed halves: no carry, every dwell < 2^14
         const uint32_t local = (t4 & 0xFFFFu) + (t4 >> 16);
         uint32_t inc = local;
@@ -743,45 +749,38 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
             if (lane >= sh) inc += v;
         }
         __syncwarp();
+        // (2a) one bit per k-mer start (the tile's first k-mer excepted: chunks before any bit belong to it)
         const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
-        uint32_t pos = inc - local + ph;  // the k-mer starts at bit (pos&7) of chunk (pos>>3)
-        uint32_t wprev = lane == 0 ? 0u : (pos + 7) >> 3;  // (chunk 0's clipped first sample falls into k-mer 0)
-        const uint32_t pos0 = pos, wprev0 = wprev;
-        uint32_t long_dwell = 0;   // becomes >= 4 when some k-mer owns the first sample of more than three chunks
+        uint32_t pos = inc - local + ph;  // frame position of the k-mer's first sample: bit (pos & 31) of entry pos >> 5
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const uint32_t dj = (j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xFFFFu);
-            const uint32_t m = (uint32_t)(m0 + j);
-            const uint32_t end = pos + dj;
-            const uint32_t wnext = (end + 7) >> 3;
-            // chunks [wprev, wnext) have their first sample inside this k-mer
-            const uint32_t n = wnext - wprev;
-            unsigned char *mp = smem + map_off + W_MAP + wprev;
-#ifdef SQG_KO_MAP
-            if (n > 1000) mp[0] = (unsigned char)m;
-            long_dwell |= n;
-            pos = end; wprev = wnext;
-            continue;
-#endif
-            if (n > 0) mp[0] = (unsigned char)m;
-            if (n > 1) mp[1] = (unsigned char)m;
-            if (n > 2) mp[2] = (unsigned char)m;
-            long_dwell |= n;
-            if (dj != 0 && m != 0)
-                atomicOr(reinterpret_cast<uint32_t *>(smem + map_off + W_BMAP + ((pos >> 5) << 2)), 1u << (pos & 31u));
-            pos = end;
-            wprev = wnext;
+            if (dj != 0 && m0 + j != 0)
+                atomicOr(reinterpret_cast<uint32_t *>(smem + map_off + W_MAP + ((pos >> 5) << 3)), 1u << (pos & 31u));
+            pos += dj;
         }
-        if (__builtin_expect(long_dwell > 3, 0)) {   // rare (dwell >= 25 samples): the remaining chunks of such k-mers
-            uint32_t ps = pos0, wp = wprev0;
+        __syncwarp();
+        // (2b) per entry: the number of starts before it (lane = 4 consecutive entries per round, warp scan, carry)
+        uint32_t carry = 0;
+        for (uint32_t e0 = 0; e0 < n_ent; e0 += 128) {
+            uint4 *ep = reinterpret_cast<uint4 *>(smem + map_off + W_MAP + 8 * (e0 + 4 * lane));
+            uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+            const bool in = e0 + 4 * lane < (uint32_t)(MAPC / 4);
+            if (in) { a = ep[0]; b = ep[1]; }
+            const uint32_t c0 = __popc(a.x), c1 = __popc(a.z), c2 = __popc(b.x), c3 = __popc(b.z);
+            const uint32_t mine = c0 + c1 + c2 + c3;
+            uint32_t run = mine;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t dj = (j & 1) ? (dw[j >> 1] >> 16) : (dw[j >> 1] & 0xFFFFu);
-                const uint32_t wn = (ps + dj + 7) >> 3;
-                for (uint32_t c = wp + 3; c < wn; c++) smem[map_off + W_MAP + c] = (unsigned char)(m0 + j);
-                ps += dj;
-                wp = wn;
+            for (int sh = 1; sh < 32; sh <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, run, sh);
+                if (lane >= sh) run += v;
             }
+            const uint32_t before = carry + run - mine;
+            if (in) {
+                ep[0] = make_uint4(a.x, before, a.z, before + c0);
+                ep[1] = make_uint4(b.x, before + c0 + c1, b.z, before + c0 + c1 + c2);
+            }
+            carry += __shfl_sync(0xffffffffu, run, 31);
         }
     } else {
         __syncwarp();
