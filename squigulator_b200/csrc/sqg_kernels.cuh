@@ -433,8 +433,11 @@ __device__ __forceinline__ uint32_t opaque_smem_addr(const void *sptr) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#ifndef SQG_ST_POLICY
+#define SQG_ST_POLICY ".cs"   // streaming (evict-first) stores: the signal is written once and never read back by the kernel
+#endif
 __device__ __forceinline__ void st_cs_v4(void *gptr, uint4 v) {
-    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.global" SQG_ST_POLICY ".v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ---- shared-memory loads of the sample loop, by absolute shared-window address with the constant part as an
