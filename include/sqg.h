@@ -107,6 +107,8 @@ void sqg_host_free(void *p);
                              slow5_ptr_compress_solo(SLOW5_COMPRESS_SVB_ZD, raw_signal, ...) gives
                              (slow5lib/src/slow5_press.c:1055-1087) - INSTEAD of raw int16: `signal` is NULL,
                              `svb`/`svb_off` are set; ~1.3 bytes per sample cross PCIe instead of 2 */
+#define SQG_WANT_SS_TEXT 0x4u /* return aln->ss already formatted as the PAF/SAM `ss:Z:` value: "d0,d1,...,dn-1," per read
+                                 (no terminator), RNA reads last k-mer first, exactly what src/format.c:69-75 appends */
 
 typedef struct {
     int64_t n_reads;
@@ -121,6 +123,8 @@ typedef struct {
     const uint8_t *svb;            /* SQG_WANT_SVB: read i's stream = svb[svb_off[i] .. svb_off[i] + svb_len[i]) */
     const int64_t *svb_off;        /* n_reads+1 (16-byte aligned starts; [n_reads] = bytes copied) */
     const int64_t *svb_len;        /* n_reads */
+    const char *ss_text;           /* SQG_WANT_SS_TEXT: read i's dwell string = ss_text[ss_text_off[i] .. ss_text_off[i+1]) */
+    const int64_t *ss_text_off;    /* n_reads+1 */
 } sqg_result_t;
 
 /* bases: the reads' characters back to back (no terminators needed); read i = bases[base_off[i] ..

@@ -489,3 +489,17 @@ int64_t sqo_svb_zd_encode(const int16_t *sig, int64_t n, uint8_t *out) {
     }
     return (int64_t)(data - out);
 }
+
+/* ------------------------------------------------------------------ ss:Z: text */
+
+/* The dwell string of a PAF/SAM record, src/format.c:69-75 (paf_str) and :114-118 (sam_str): "%d," per k-mer,
+ * last k-mer first for RNA (t_st > t_end).  out needs 12*n bytes; no terminator is written.  Returns the length. */
+#include <stdio.h>
+int64_t sqo_ss_text(const int32_t *ss, int64_t n, int rna, char *out) {
+    char *p = out;
+    for (int64_t i = 0; i < n; i++) {
+        int64_t idx = rna ? n - i - 1 : i;
+        p += sprintf(p, "%d,", ss[idx]);
+    }
+    return (int64_t)(p - out);
+}

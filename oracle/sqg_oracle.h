@@ -75,6 +75,7 @@ void sqo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, ui
 float sqo_z32(const void *ztable, uint32_t idx, const uint32_t key[2], uint32_t c0, uint32_t c1, uint32_t c2,
               uint32_t tail_stream);
 float sqo_fma_rz(float x, float y, float z);            /* PTX fma.rz.f32, restated */
+int64_t sqo_ss_text(const int32_t *ss, int64_t n, int rna, char *out);     /* src/format.c:69-75 */
 int64_t sqo_svb_zd_encode(const int16_t *sig, int64_t n, uint8_t *out); /* slow5lib/src/slow5_press.c:1055-1087 */
 
 #ifdef __cplusplus

@@ -223,6 +223,19 @@ def parse_paf_ss(path, rna):
     return out
 
 
+def write_ss_text(out_dir):
+    """tests/golden/ss_text.json: the `ss:Z:` values of the reference's own PAF goldens, verbatim (src/format.c:69-75),
+    keyed by fixture name - pins the dwell-string format (SQG_WANT_SS_TEXT, oracle sqo_ss_text)."""
+    import json
+    d = {}
+    for name, _, _, paf_exp in CASES:
+        if paf_exp:
+            d[name] = [[t for t in line.rstrip("\n").split("\t") if t.startswith("ss:Z:")][0][5:]
+                       for line in open(os.path.join(REF, paf_exp))]
+    json.dump(d, open(os.path.join(out_dir, "ss_text.json"), "w"))
+    return d
+
+
 def dump_meth_model(lib, path):
     """Write the reference's compiled-in R10 CpG 9-mer table as an f5c-style model file so the CLI can
     load it through --meth-model (read_model, src/model.c:40-142)."""
@@ -245,6 +258,7 @@ def dump_meth_model(lib, path):
 
 
 def main():
+    write_ss_text(OUT)
     only = set(sys.argv[1:])
     lib = load_ref()
     os.makedirs(OUT, exist_ok=True)

@@ -11,6 +11,7 @@ SQ_RNA, SQ_FULL_CONTIG, SQ_IDEAL, SQ_IDEAL_TIME, SQ_IDEAL_AMP, SQ_PREFIX, SQ_R10
 RNG_PHILOX, RNG_LEGACY = 0, 1
 WANT_SS = 0x1
 WANT_SVB = 0x2
+WANT_SS_TEXT = 0x4
 
 PROFILE_FIELDS = ("digitisation", "sample_rate", "bps", "range", "offset_mean", "offset_std",
                   "median_before_mean", "median_before_std", "dwell_mean", "dwell_std")
@@ -57,7 +58,8 @@ class Result(C.Structure):
                 ("sig_off", C.POINTER(C.c_int64)), ("len_raw_signal", C.POINTER(C.c_int64)),
                 ("offset", C.POINTER(C.c_double)), ("median_before", C.POINTER(C.c_double)),
                 ("ss", C.POINTER(C.c_int32)), ("ss_off", C.POINTER(C.c_int64)),
-                ("svb", C.POINTER(C.c_uint8)), ("svb_off", C.POINTER(C.c_int64)), ("svb_len", C.POINTER(C.c_int64))]
+                ("svb", C.POINTER(C.c_uint8)), ("svb_off", C.POINTER(C.c_int64)), ("svb_len", C.POINTER(C.c_int64)),
+                ("ss_text", C.POINTER(C.c_char)), ("ss_text_off", C.POINTER(C.c_int64))]
 
 
 class SqgError(RuntimeError):
@@ -169,9 +171,14 @@ class SignalGenerator:
             vo = np.ctypeslib.as_array(res.svb_off, shape=(n + 1,))
             vl = np.ctypeslib.as_array(res.svb_len, shape=(n,))
             svb = np.ctypeslib.as_array(res.svb, shape=(max(int(vo[-1]), 1),))
+        if res.ss_text:  # SQG_WANT_SS_TEXT: the PAF/SAM `ss:Z:` value of every read
+            to = np.ctypeslib.as_array(res.ss_text_off, shape=(n + 1,))
+            txt = C.string_at(res.ss_text, int(to[-1]))
         out = []
         for i in range(n):
             d = dict(offset=float(o[i]), median_before=float(mb[i]), n_samples=int(ln[i]))
+            if res.ss_text:
+                d["ss_text"] = txt[to[i]:to[i + 1]]
             if sig is not None:
                 s = sig[off[i]:off[i] + ln[i]]
                 d["sig"] = s.copy() if copy else s
@@ -183,11 +190,12 @@ class SignalGenerator:
         return out
 
     # -- the batch call (process_db's fan-out, reference src/sim.c:622)
-    def gen_batch(self, reads, first_read_index=0, want_ss=False, want_svb=False):
+    def gen_batch(self, reads, first_read_index=0, want_ss=False, want_svb=False, want_ss_text=False):
         bases, off = _pack_reads(reads)
         res = Result()
         self._check(self.lib.sqg_gen_batch(self.h, len(reads), bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
-                                           first_read_index, (WANT_SS if want_ss else 0) | (WANT_SVB if want_svb else 0), C.byref(res)))
+                                           first_read_index, (WANT_SS if want_ss else 0) | (WANT_SVB if want_svb else 0) | (WANT_SS_TEXT if want_ss_text else 0),
+                                           C.byref(res)))
         return self._unpack(res)
 
     def gen_batch_raw(self, bases, off, first_read_index=0, want=0):

@@ -28,6 +28,7 @@
 #include "sqg_kernels.cuh"
 #include "sqg_legacy.cuh"
 #include "sqg_svb.cuh"
+#include "sqg_sstext.cuh"
 
 extern "C" const unsigned char sqg_ztable_blob[];  // Z32 ++ Z2 (binary32), embedded from data/ztable_v3.bin (ztable_blob.S)
 
@@ -115,6 +116,11 @@ struct Slot {
     PinBuf<int64_t> h_svb_len, h_svb_off;
     PinBuf<uint8_t> h_svb;
     int64_t svb_bytes = 0;
+    DevBuf<int64_t> d_sst_len, d_sst_off, d_ss_off;   // SQG_WANT_SS_TEXT
+    DevBuf<char> d_sst;
+    PinBuf<int64_t> h_sst_off;
+    PinBuf<char> h_sst;
+    int64_t sst_bytes = 0;
     // SQG_RNG_LEGACY scratch (per k-mer of the batch)
     DevBuf<uint32_t> d_rank, d_rank_sorted, d_idx, d_idx_sorted;
     DevBuf<uint64_t> d_dsorted, d_excl, d_heads, d_segstart, d_cpos;
@@ -141,6 +147,7 @@ struct Slot {
         h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
         h_ss.release();
         d_svb_len.release(); d_svb_off.release(); d_svb.release(); h_svb_len.release(); h_svb_off.release(); h_svb.release();
+        d_sst_len.release(); d_sst_off.release(); d_ss_off.release(); d_sst.release(); h_sst_off.release(); h_sst.release();
         for (auto e : kev) cudaEventDestroy(e);
         kev.clear();
         if (ev0) cudaEventDestroy(ev0);
@@ -358,7 +365,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     CU(s.d_median.ensure(nr, false, s.stream));
     CU(s.d_meta.ensure(4, false, s.stream));
     CU(s.h_meta.ensure(4));
-    if ((want & SQG_WANT_SS) || ctx->legacy) CU(s.d_ss.ensure((size_t)std::max<int64_t>(nk_total, 1), false, s.stream));
+    if ((want & (SQG_WANT_SS | SQG_WANT_SS_TEXT)) || ctx->legacy) CU(s.d_ss.ensure((size_t)std::max<int64_t>(nk_total, 1), false, s.stream));
     return SQG_OK;
 }
 
@@ -371,7 +378,7 @@ GenParams slot_params(sqg_ctx *ctx, Slot &s) {
     p.sig = s.d_sig.p; p.ss = s.d_ss.p;
     p.n_reads = (int32_t)s.n_reads; p.n_segs = (int32_t)s.n_segs; p.n_tiles = (int32_t)s.n_tiles;
     p.first_read = s.first_read;
-    p.want_ss = (s.want & SQG_WANT_SS) ? 1 : 0;
+    p.want_ss = (s.want & (SQG_WANT_SS | SQG_WANT_SS_TEXT)) ? 1 : 0;
     return p;
 }
 
@@ -528,6 +535,34 @@ int slot_compress(sqg_ctx *ctx, Slot &s) {
     return SQG_OK;
 }
 
+// SQG_WANT_SS_TEXT: the dwell strings of the batch's reads, in HBM (sqg_sstext.cuh).
+int slot_sstext(sqg_ctx *ctx, Slot &s) {
+    s.sst_bytes = 0;
+    if (s.n_reads == 0) return SQG_OK;
+    const size_t n = (size_t)s.n_reads;
+    CU(s.d_sst_len.ensure(n, false, s.stream));
+    CU(s.d_sst_off.ensure(n + 1, false, s.stream));
+    CU(s.d_ss_off.ensure(n + 1, false, s.stream));
+    CU(s.h_sst_off.ensure(n + 1));
+    CU(cudaMemcpyAsync(s.d_ss_off.p, s.h_ss_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+    SsTextParams q;
+    q.ss = s.d_ss.p; q.ss_off = s.d_ss_off.p; q.len = s.d_sst_len.p; q.off = s.d_sst_off.p; q.text = nullptr;
+    q.n_reads = (int32_t)s.n_reads; q.reversed = ctx->rev ? 1 : 0;
+    sstext_size_kernel<<<(int)s.n_reads, SST_THREADS, 0, s.stream>>>(q);
+    sstext_offsets_kernel<<<1, 1024, 0, s.stream>>>(q);
+    CU(cudaMemcpyAsync(s.h_sst_off.p, s.d_sst_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    s.sst_bytes = s.h_sst_off.p[n];
+    CU(s.d_sst.ensure((size_t)std::max<int64_t>(s.sst_bytes, 16), false, s.stream));
+    CU(s.h_sst.ensure((size_t)std::max<int64_t>(s.sst_bytes, 16)));
+    q.text = s.d_sst.p;
+    sstext_write_kernel<<<(int)s.n_reads, SST_THREADS, 0, s.stream>>>(q);
+    CU(cudaMemcpyAsync(s.h_sst.p, s.d_sst.p, (size_t)s.sst_bytes, cudaMemcpyDeviceToHost, s.stream));
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return SQG_OK;
+}
+
 // D2H of everything the caller gets back; fills *res.  Synchronises the slot's stream.
 int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     const size_t n = (size_t)s.n_reads;
@@ -576,6 +611,8 @@ int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
         res->svb = svb ? s.h_svb.p : nullptr;
         res->svb_off = svb ? s.h_svb_off.p : nullptr;
         res->svb_len = svb ? s.h_svb_len.p : nullptr;
+        res->ss_text = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst.p : nullptr;
+        res->ss_text_off = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst_off.p : nullptr;
     }
     return SQG_OK;
 }
@@ -588,6 +625,7 @@ int slot_run_all(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
     if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
     if ((want & SQG_WANT_SVB) && (rc = slot_compress(ctx, s)) != SQG_OK) return rc;
+    if ((want & SQG_WANT_SS_TEXT) && (rc = slot_sstext(ctx, s)) != SQG_OK) return rc;
     return slot_fetch(ctx, s, res);
 }
 
@@ -900,6 +938,8 @@ int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res) {
         res->svb = svb ? s.h_svb.p : nullptr;
         res->svb_off = svb ? s.h_svb_off.p : nullptr;
         res->svb_len = svb ? s.h_svb_len.p : nullptr;
+        res->ss_text = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst.p : nullptr;
+        res->ss_text_off = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst_off.p : nullptr;
     }
     return SQG_OK;
 }
@@ -1016,6 +1056,10 @@ int sqg_dev_batch_fetch(sqg_ctx_t *ctx, sqg_dev_batch_t *b, sqg_result_t *res) {
     CU(cudaSetDevice(ctx->device));
     if (b->slot.want & SQG_WANT_SVB) {
         int rc = slot_compress(ctx, b->slot);
+        if (rc != SQG_OK) return rc;
+    }
+    if (b->slot.want & SQG_WANT_SS_TEXT) {
+        int rc = slot_sstext(ctx, b->slot);
         if (rc != SQG_OK) return rc;
     }
     return slot_fetch(ctx, b->slot, res);

@@ -67,6 +67,8 @@ def load_oracle():
     lib.sqo_z32.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.sqo_fma_rz.restype = C.c_float
     lib.sqo_fma_rz.argtypes = [C.c_float, C.c_float, C.c_float]
+    lib.sqo_ss_text.restype = C.c_int64
+    lib.sqo_ss_text.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     lib.sqo_svb_zd_encode.restype = C.c_int64
     lib.sqo_svb_zd_encode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.sqo_kmer_rank.restype = C.c_uint32
@@ -210,3 +212,11 @@ def svb_zd_decode(buf):
     v = v.astype(np.int64)
     d = (v >> 1) ^ -(v & 1)
     return np.cumsum(d).astype(np.int16), int(start[-1] + nb[-1]) if n else 4
+
+
+def oracle_ss_text(lib, ss, rna):
+    """the `ss:Z:` value of a PAF/SAM record for one read's dwell array, by the oracle's restatement of src/format.c"""
+    ss = np.ascontiguousarray(ss, dtype=np.int32)
+    out = np.empty(12 * ss.size + 16, dtype=np.uint8)
+    n = lib.sqo_ss_text(ss.ctypes.data_as(C.c_void_p), ss.size, int(bool(rna)), out.ctypes.data_as(C.c_void_p))
+    return out[:n].tobytes()

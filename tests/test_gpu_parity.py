@@ -144,6 +144,30 @@ def test_svb_zd_streams(sq, oracle_lib):
         assert np.array_equal(b["svb"], H.oracle_svb_zd(oracle_lib, a["sig"]))
 
 
+def test_ss_text(sq, oracle_lib):
+    """SQG_WANT_SS_TEXT: the `ss:Z:` value of every read, formatted on the GPU == the oracle's restatement of
+    src/format.c:69-75 applied to the dwell array of the same read (DNA in k-mer order, RNA last k-mer first)."""
+    reads = H.random_reads(20, 2500, seed=43, min_len=0) + [b"", b"A", b"ACGTACGTAC", b"ACGT" * 4000]
+    for prof, k, kw in (("dna-r10-prom", 9, {}), ("rna-r9-prom", 5, {}), ("rna004-prom", 9, {}),
+                        ("dna-r9-prom", 6, dict(flags=H.SQ_IDEAL_TIME))):
+        gen = sq.SignalGenerator(prof, H.random_model(4 ** k), k, seed=9, **kw)
+        a = gen.gen_batch(reads, first_read_index=5, want_ss=True)
+        b = gen.gen_batch(reads, first_read_index=5, want_ss_text=True)
+        rna = gen_is_rna = prof.startswith("rna")
+        gen.close()
+        for x, y in zip(a, b):
+            assert np.array_equal(x["sig"], y["sig"])
+            assert y["ss_text"] == H.oracle_ss_text(oracle_lib, x["ss"], rna), (prof, len(x["ss"]))
+    # large dwells (3-4 digits; the library caps mean + 6 std at 1200 samples per k-mer)
+    prof = dict(H.PRESETS["dna-r9-prom"][0], dwell_mean=850.0, dwell_std=55.0)
+    gen = sq.SignalGenerator(prof, H.random_model(4096), 6, seed=9)
+    a = gen.gen_batch(reads[:4], want_ss=True); b = gen.gen_batch(reads[:4], want_ss_text=True, want_svb=True)
+    gen.close()
+    for x, y in zip(a, b):
+        assert y["ss_text"] == H.oracle_ss_text(oracle_lib, x["ss"], False)
+        assert np.array_equal(y["svb"], H.oracle_svb_zd(oracle_lib, x["sig"]))
+
+
 def test_batch_split_and_api_variants_agree(sq):
     """Output depends only on (seed, global read index, bases): not on batching, nor on which entry point is used."""
     reads = H.random_reads(24, 2500, seed=21, min_len=0)

@@ -43,3 +43,20 @@ def test_round_trip(oracle_lib):
         dec, used = H.svb_zd_decode(enc)
         assert used == enc.size
         assert np.array_equal(dec, sig)
+
+
+def test_ss_text_equals_reference_goldens(oracle_lib):
+    """the dwell string of PAF/SAM records.  The oracle's restatement of src/format.c:69-75, fed with
+    the dwell arrays of the reference's PAF goldens, reproduces their `ss:Z:` values verbatim (RNA: last k-mer first)."""
+    import json
+    texts = json.load(open(os.path.join(H.GOLDEN_DIR, "ss_text.json")))
+    assert set(texts) == {"dna_r10_paf", "rna_r9_paf"}
+    for name, lines in texts.items():
+        g = H.Golden(os.path.join(H.GOLDEN_DIR, name + ".npz"))
+        rna = bool(g.cfg["flags"] & H.SQ_RNA)
+        assert len(lines) == len(g.ss)
+        for ss, want in zip(g.ss, lines):
+            assert H.oracle_ss_text(oracle_lib, ss, rna) == want.encode()
+    assert H.oracle_ss_text(oracle_lib, np.array([1, 10, 100, 1000, 7], np.int32), False) == b"1,10,100,1000,7,"
+    assert H.oracle_ss_text(oracle_lib, np.array([1, 10, 100], np.int32), True) == b"100,10,1,"
+    assert H.oracle_ss_text(oracle_lib, np.zeros(0, np.int32), False) == b""
