@@ -737,6 +737,29 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
         }
     }
 
+    // (1b) base-4 models: the four (k+1)-mer gathers of this lane are issued now, so that their L2 latency runs under
+    // the shared-memory work of step (2).  16 two-bit digits packed first-digit-most-significant
+    // (((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes); k-mers 2j, 2j+1 of the lane = the two k-mers of the
+    // (k+1)-mer at digit 2j: ONE 16-byte gather for both.  The four pairs are visited in ROTATED order
+    // jj(j) = (j + lane/2) & 3 so that the 16-byte parameter stores of a quarter-warp fall into 8 different bank groups.
+    float4 mv4[4];
+    const int rot4 = lane >> 1;
+    if (!METH) {
+        __syncwarp();
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
+        const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
+                           ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
+        const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
+        const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t r = (P >> (sh0 - 4 * ((j + rot4) & 3))) & pmask;
+            if (nk_tile < TK && m0 + 2 * ((j + rot4) & 3) >= nk_tile) r = 0;
+            mv4[j] = __ldg(&p.pair_model[r]);
+        }
+    }
+
     // (2) warp scan of the dwells, then the chunk -> k-mer map and the boundary bitmap
     if (RAND_DWELL) {
         const uint4 dq = *reinterpret_cast<const uint4 *>(smem + map_off + W_DWELL + lane * 16);
@@ -789,7 +812,8 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
         __syncwarp();
     }
 
-    // (3) ranks of this lane's 8 k-mers (src/seq.h:31-42 / :62-74), (4) their parameters from (level_mean, level_stdv)
+    // (3) the parameters of this lane's 8 k-mers from (level_mean, level_stdv); base-5 (CpG) models: ranks
+    // (src/seq.h:62-74) and single gathers here
     const float scale_f = (float)p.scale, off_f = (float)td.offset;
     auto make_par = [&](float mean, float stdv) -> float2 {
         if (NOISY) {
@@ -804,33 +828,17 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
         }
     };
     {
-        const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
-        const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
         if (!METH) {
-            // 16 two-bit digits packed first-digit-most-significant: ((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes.
-            // k-mers 2j, 2j+1 of the lane = the two k-mers of the (k+1)-mer at digit 2j: ONE 16-byte gather for both.
-            // The four pairs are visited in ROTATED order jj(j) = (j + lane/2) & 3 so that the 16-byte parameter stores
-            // of a quarter-warp fall into 8 different bank groups.
-            const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
-                               ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
-            const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
-            const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
-            const int rot = lane >> 1;
-            float4 mv[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t r = (P >> (sh0 - 4 * ((j + rot) & 3))) & pmask;
-                if (nk_tile < TK && m0 + 2 * ((j + rot) & 3) >= nk_tile) r = 0;
-                mv[j] = __ldg(&p.pair_model[r]);
-            }
             if (m0 < nk_tile) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float2 pa = make_par(mv[j].x, mv[j].y), pb = make_par(mv[j].z, mv[j].w);
-                    *reinterpret_cast<float4 *>(smem + par_off + 8 * (m0 + 2 * ((j + rot) & 3))) = make_float4(pa.x, pa.y, pb.x, pb.y);
+                    const float2 pa = make_par(mv4[j].x, mv4[j].y), pb = make_par(mv4[j].z, mv4[j].w);
+                    *reinterpret_cast<float4 *>(smem + par_off + 8 * (m0 + 2 * ((j + rot4) & 3))) = make_float4(pa.x, pa.y, pb.x, pb.y);
                 }
             }
         } else {
+            const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
+            const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
             const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
             const int km1 = p.k - 1;
             uint32_t rank = 0, ranks[8];
