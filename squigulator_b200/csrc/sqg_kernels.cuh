@@ -380,7 +380,8 @@ constexpr uint32_t W_DESC = W_DWELL + TK * 2;        // two TileDesc slots
 constexpr uint32_t W_SIGOFF = W_DESC + 2 * 80;       // two int64 slots
 constexpr uint32_t WARP_BYTES = W_SIGOFF + 16;
 constexpr uint32_t SM_PAR = 0;
-constexpr uint32_t SM_Z = SM_PAR + K4_WARPS * TK * 8;          // (128-byte aligned)
+constexpr uint32_t PAR_BYTES = TK * 8 + 48;   // + rows the sample loop may load (never use) past the tile's last k-mer; 16-byte multiple
+constexpr uint32_t SM_Z = (SM_PAR + K4_WARPS * PAR_BYTES + 127) & ~127u;
 constexpr uint32_t SM_CODE = SM_Z + Z32_BYTES;
 constexpr uint32_t SM_MBAR = SM_CODE + 256;
 constexpr uint32_t SM_WARP = SM_MBAR + 16;
@@ -877,7 +878,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     unsigned long long *stage_bar = reinterpret_cast<unsigned long long *>(smem + SM_MBAR);
-    const uint32_t par_off = SM_PAR + (uint32_t)warp * (TK * 8);
+    const uint32_t par_off = SM_PAR + (uint32_t)warp * PAR_BYTES;
     const uint32_t map_off = SM_WARP + (uint32_t)warp * WARP_BYTES;
     const uint32_t wbase = opaque_smem_addr(smem + map_off);  // this warp's buffer, for the asynchronous copies
 
