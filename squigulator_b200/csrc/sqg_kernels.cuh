@@ -718,24 +718,78 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
     const uint32_t ph = REV ? ((B - L) & 7u) : (B & 7u);
     const int m0 = lane * 8;
 
-    // (1) bases -> digits (the code table folds IUPAC letters, src/seq.h:14-28 / :45-60)
-    if (!tile_is_junction(p, td.a_rem, nk_tile)) {
+    // (1) bases -> digits.  Fast path (base-4 models, window in one piece): every lane takes the 16 raw bytes of its own
+    // 8 k-mers straight from the prefetched window (three aligned 8-byte loads + a funnel shift by the window's
+    // misalignment) and turns A/C/G/T of either case into digits arithmetically, ((c>>1) ^ (c>>2)) & 3, four bytes at
+    // a time; a PRMT maps the digits back to letters to check that every byte really was one of those eight.  Any
+    // other byte in the tile (IUPAC codes, U, N: src/seq.h:14-28 folds them) sends the whole warp through the
+    // 256-entry code table, which is also the path of base-5 (CpG) models (src/seq.h:45-60) and of prefix junctions.
+    uint32_t dg[4] = {0, 0, 0, 0};   // the lane's 16 digits, one per byte
+    bool table_path = METH || tile_is_junction(p, td.a_rem, nk_tile);
+    if (!table_path) {
         const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
-        const uint32_t raw_off = map_off + W_RAW + shift + lane;
+        const uint32_t s0 = shift + 8u * (uint32_t)lane;     // lane's first byte within the raw buffer
+        const uint2 *rw = reinterpret_cast<const uint2 *>(smem + map_off + W_RAW + (s0 & ~7u));
+        const uint2 w0 = rw[0], w1 = rw[1], w2 = rw[2];
+        const bool hi = (s0 & 4u) != 0;                       // (warp-uniform: shift & 4)
+        const uint32_t q0 = hi ? w0.y : w0.x, q1 = hi ? w1.x : w0.y, q2 = hi ? w1.y : w1.x, q3 = hi ? w2.x : w1.y, q4 = hi ? w2.y : w2.x;
+        const uint32_t fs = 8u * (s0 & 3u);
+        const uint32_t x[4] = {__funnelshift_r(q0, q1, fs), __funnelshift_r(q1, q2, fs), __funnelshift_r(q2, q3, fs), __funnelshift_r(q3, q4, fs)};
+        uint32_t bad = 0;
 #pragma unroll
-        for (int u = 0; u < WIN_LOADS; u++) {
-            const int i = lane + 32 * u;
-            if (i < nb) {
-                const uint32_t c = smem[SM_CODE + smem[raw_off + 32 * u]];
+        for (int i = 0; i < 4; i++) {
+            const uint32_t c = ((x[i] >> 1) ^ (x[i] >> 2)) & 0x03030303u;
+            const uint32_t t = (c | (c >> 4)) & 0x00FF00FFu;
+            const uint32_t sel = (t | (t >> 8)) & 0xFFFFu;                    // the four digits as PRMT selectors
+            bad |= __byte_perm(0x54474341u /* "ACGT" */, 0u, sel) ^ (x[i] & 0xDFDFDFDFu);
+            dg[i] = c;
+        }
+        // bytes past the window's end are whatever the 16-byte granules held: harmless as digits, but they must not
+        // force the table path, so only the lane's bytes inside the window count
+        const int inside = nb - 8 * lane;
+        if (inside < 16) {
+            if (inside <= 0) bad = 0;
+            else {
+                // re-derive per word: keep the flags of the first `inside` bytes
+                uint32_t keep = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int nbytes = min(max(inside - 4 * i, 0), 4);
+                    const uint32_t m = nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+                    const uint32_t c = dg[i];
+                    const uint32_t t = (c | (c >> 4)) & 0x00FF00FFu;
+                    const uint32_t sel = (t | (t >> 8)) & 0xFFFFu;
+                    keep |= (__byte_perm(0x54474341u, 0u, sel) ^ (x[i] & 0xDFDFDFDFu)) & m;
+                }
+                bad = keep;
+            }
+        }
+        table_path = __any_sync(0xffffffffu, bad != 0);
+    }
+    if (table_path) {
+        if (!tile_is_junction(p, td.a_rem, nk_tile)) {
+            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
+            const uint32_t raw_off = map_off + W_RAW + shift + lane;
+#pragma unroll 1
+            for (int u = 0; u < WIN_LOADS; u++) {
+                const int i = lane + 32 * u;
+                if (i < nb) {
+                    const uint32_t c = smem[SM_CODE + smem[raw_off + 32 * u]];
+                    smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = lane; i < nb; i += 32) {
+                const uint32_t c = smem[SM_CODE + __ldg(p.bases + (i < td.a_rem ? td.a_off : td.b_off) + i)];
                 smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
             }
         }
-    } else {
-#pragma unroll 1
-        for (int i = lane; i < nb; i += 32) {
-            const uint32_t c = smem[SM_CODE + __ldg(p.bases + (i < td.a_rem ? td.a_off : td.b_off) + i)];
-            smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
-        }
+        __syncwarp();
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
+        dg[0] = dwa.x; dg[1] = dwa.y; dg[2] = dwb.x; dg[3] = dwb.y;
+        __syncwarp();   // (the digit buffer is rewritten by this warp's next tile)
     }
 
     // (1b) base-4 models: the four (k+1)-mer gathers of this lane are issued now, so that their L2 latency runs under
@@ -746,11 +800,8 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
     float4 mv4[4];
     const int rot4 = lane >> 1;
     if (!METH) {
-        __syncwarp();
-        const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
-        const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
-        const uint32_t P = ((((dwa.x & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dwa.y & 0x03030303u) * 0x40100401u) >> 24) << 16) |
-                           ((((dwb.x & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dwb.y & 0x03030303u) * 0x40100401u) >> 24);
+        const uint32_t P = ((((dg[0] & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dg[1] & 0x03030303u) * 0x40100401u) >> 24) << 16) |
+                           ((((dg[2] & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dg[3] & 0x03030303u) * 0x40100401u) >> 24);
         const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
         const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
 #pragma unroll
@@ -838,9 +889,7 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
                 }
             }
         } else {
-            const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
-            const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
-            const uint32_t dw[4] = {dwa.x, dwa.y, dwb.x, dwb.y};
+            const uint32_t dw[4] = {dg[0], dg[1], dg[2], dg[3]};
             const int km1 = p.k - 1;
             uint32_t rank = 0, ranks[8];
 #pragma unroll
