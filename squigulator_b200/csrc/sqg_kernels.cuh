@@ -578,7 +578,11 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned cha
         }
         if (!RAND_DWELL) chunk_kmers<RAND_DWELL>(p, smem, map_off, t, w, k0, m1);
         const uint32_t par0 = k0 * 8 + par_off;
+#ifdef SQG_KO_PAR
+        const float2 q0 = lds_f2<0>(par_off + 8 * (w & 1)), q1 = q0, q2 = q0;
+#else
         const float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0), q2 = lds_f2<16>(par0);
+#endif
         const uint32_t t1 = m1 - 1u;        // bit j clear  <=>  slot j lies at or after the 1st boundary
         const uint32_t m2 = m1 & t1;        // boundaries after the first
         const uint32_t t2 = m2 - 1u;        // bit j clear  <=>  slot j lies at or after the 2nd boundary
@@ -808,7 +812,11 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
         for (int j = 0; j < 4; j++) {
             uint32_t r = (P >> (sh0 - 4 * ((j + rot4) & 3))) & pmask;
             if (nk_tile < TK && m0 + 2 * ((j + rot4) & 3) >= nk_tile) r = 0;
+#ifdef SQG_KO_GATHER
+            mv4[j] = __ldg(&p.pair_model[(r & 0x3F) * 0 + ((td.kidx0 >> 3) & 0xFF) * 128 + j * 32 + lane]);   // coalesced (timing only)
+#else
             mv4[j] = __ldg(&p.pair_model[r]);
+#endif
         }
     }
 
@@ -827,6 +835,7 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
             if (lane >= sh) inc += v;
         }
         __syncwarp();
+#ifndef SQG_KO_MAP
         // (2a) one bit per k-mer start (the tile's first k-mer excepted: chunks before any bit belong to it)
         const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
         uint32_t pos = inc - local + ph;  // frame position of the k-mer's first sample: bit (pos & 31) of entry pos >> 5
@@ -860,6 +869,7 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
             }
             carry += __shfl_sync(0xffffffffu, run, 31);
         }
+#endif
     } else {
         __syncwarp();
     }
