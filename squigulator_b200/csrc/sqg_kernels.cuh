@@ -847,27 +847,30 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
             pos += dj;
         }
         __syncwarp();
-        // (2b) per entry: the number of starts before it (lane = 4 consecutive entries per round, warp scan, carry)
+        // (2b) per entry: the number of starts before it.  Per round of 128 entries a lane takes entries 2l, 2l+1 and
+        // 64+2l, 64+2l+1 (two conflict-free 16-byte accesses); the two halves are scanned together, their counts packed
+        // in the halves of one register (every count < 2^16).
         uint32_t carry = 0;
         for (uint32_t e0 = 0; e0 < n_ent; e0 += 128) {
-            uint4 *ep = reinterpret_cast<uint4 *>(smem + map_off + W_MAP + 8 * (e0 + 4 * lane));
+            uint4 *ep = reinterpret_cast<uint4 *>(smem + map_off + W_MAP + 8 * e0 + 16 * lane);
+            const bool in1 = e0 + 2 * lane < (uint32_t)(MAPC / 4), in2 = e0 + 64 + 2 * lane < (uint32_t)(MAPC / 4);
             uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-            const bool in = e0 + 4 * lane < (uint32_t)(MAPC / 4);
-            if (in) { a = ep[0]; b = ep[1]; }
+            if (in1) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(smem_u32(ep)) : "memory");
+            if (in2) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(smem_u32(ep + 32)) : "memory");
             const uint32_t c0 = __popc(a.x), c1 = __popc(a.z), c2 = __popc(b.x), c3 = __popc(b.z);
-            const uint32_t mine = c0 + c1 + c2 + c3;
+            const uint32_t mine = (c0 + c1) | ((c2 + c3) << 16);
             uint32_t run = mine;
 #pragma unroll
             for (int sh = 1; sh < 32; sh <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, run, sh);
                 if (lane >= sh) run += v;
             }
-            const uint32_t before = carry + run - mine;
-            if (in) {
-                ep[0] = make_uint4(a.x, before, a.z, before + c0);
-                ep[1] = make_uint4(b.x, before + c0 + c1, b.z, before + c0 + c1 + c2);
-            }
-            carry += __shfl_sync(0xffffffffu, run, 31);
+            const uint32_t tot = __shfl_sync(0xffffffffu, run, 31);
+            const uint32_t before1 = carry + (run & 0xFFFFu) - (c0 + c1);
+            const uint32_t before2 = carry + (tot & 0xFFFFu) + (run >> 16) - (c2 + c3);
+            if (in1) ep[0] = make_uint4(a.x, before1, a.z, before1 + c0);
+            if (in2) ep[32] = make_uint4(b.x, before2, b.z, before2 + c2);
+            carry += (tot & 0xFFFFu) + (tot >> 16);
         }
 #endif
     } else {
