@@ -335,6 +335,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 

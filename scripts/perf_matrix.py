@@ -7,7 +7,12 @@ import squigulator_b200 as sq
 from squigulator_b200.api import PROFILES
 from bench import synth_reads, synth_model
 
+import json
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] * 1e9
+except Exception:
+    PEAK = 6650e9   # B200_PROFILING.md fallback
 bases, off = synth_reads(n_reads, 10000, False, seed=1)
 rows = []
 for prof, k in (("dna-r10-prom", 9), ("dna-r9-prom", 6)):
@@ -19,6 +24,6 @@ for prof, k in (("dna-r10-prom", 9), ("dna-r9-prom", 6)):
         t, tk = g.dev_batch_run(b, 10)
         info = g.dev_batch_info(b)
         print(f"{prof:14s} {name:11s} samples={info['samples']/1e9:.3f}G step={t/10:.3f} ms kernel={tk/10:.3f} ms "
-              f"-> {info['samples']/(tk/10*1e-3)/1e9:.0f} Gsamples/s ({2.08*info['samples']/(tk/10*1e-3)/6552.6e9*100:.1f}% of HBM roofline)")
+              f"-> {info['samples']/(tk/10*1e-3)/1e9:.0f} Gsamples/s ({2.08*info['samples']/(tk/10*1e-3)/PEAK*100:.1f}% of HBM roofline)")
         g.dev_batch_destroy(b)
         g.close()

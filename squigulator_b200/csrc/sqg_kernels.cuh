@@ -178,18 +178,29 @@ __global__ void __launch_bounds__(K1_THREADS, 1) dwell_kernel(const __grid_const
     mbar_wait(bar, 0);
     const int lane = threadIdx.x & 31;
     const int nw = K1_THREADS / 32;
-    for (int tile = blockIdx.x * nw + (threadIdx.x >> 5); tile < p.n_tiles; tile += gridDim.x * nw) {
-        const TileDesc *td = p.tiles + tile;
-        const int nk_tile = td->nk;
-        const RngKey key{p.key0, p.key1, td->r_lo, td->r_hi};
+    const int tile0 = blockIdx.x * nw + (threadIdx.x >> 5), tstride = gridDim.x * nw;
+    if (tile0 >= p.n_tiles) return;
+    // the descriptor words of the NEXT tile are loaded one iteration ahead (the kernel is otherwise bound by this latency)
+    const uint4 *q0 = reinterpret_cast<const uint4 *>(p.tiles + tile0);
+    uint4 nb = __ldg(q0 + 1), nc = __ldg(q0 + 2), ne = __ldg(q0 + 4);
+    for (int tile = tile0; tile < p.n_tiles; tile += tstride) {
+        const uint4 b = nb, c = nc, e = ne;
+        {
+            const uint4 *qn = reinterpret_cast<const uint4 *>(p.tiles + min(tile + tstride, p.n_tiles - 1));
+            nb = __ldg(qn + 1); nc = __ldg(qn + 2); ne = __ldg(qn + 4);
+        }
+        const int nk_tile = (int)b.y;
+        const uint32_t kidx0 = b.w;
+        const int64_t ss_pos = (int64_t)(((uint64_t)c.y << 32) | c.x);
+        const RngKey key{p.key0, p.key1, e.x, e.y};
         uint32_t sum = 0;
         uint32_t d[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) d[j] = 0;
         if (lane * 8 < nk_tile) {
-            const uint32_t blk = (td->kidx0 >> 3) + lane;
+            const uint32_t blk = (kidx0 >> 3) + lane;
             const uint4 w = philox4x32_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
-            const int64_t ss0 = td->ss_pos + lane * 8;
+            const int64_t ss0 = ss_pos + lane * 8;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t off = z_offset(draw_word(w, j), (blk & 31u) << 2);
