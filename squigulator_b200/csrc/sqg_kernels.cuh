@@ -13,6 +13,8 @@
 //
 // Reference statements: src/gensig.c:226-288 (gen_sig_core_seq), :293-343 (gen_sig_core), :346-356 (gen_sig).
 #pragma once
+#include <type_traits>
+
 #include "sqg_device.cuh"
 
 namespace sqg {
@@ -572,9 +574,12 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned cha
         if (NOISY) r4n = philox4x32_rk(REV ? t.C0 - w : t.C0 + w, t.r_lo, t.r_hi, ST_AMP, p.rk);
         if (RAND_DWELL) entn = lds_u2<W_MAP>(ent_lane);
     }
-    for (uint32_t wb = 0; wb < nW; wb += 32) {   // wb is warp-uniform: 32 consecutive chunks per iteration
+    // One iteration = 32 consecutive chunks (wb is warp-uniform).  EDGE iterations hold a clipped chunk or run past the
+    // tile's end; all others - the bulk - carry no bounds logic at all.
+    auto iteration = [&](const uint32_t wb, auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
         const uint32_t w = wb + lane;
-        if (w >= nW) break;
+        if (EDGE && w >= nW) return;
         const uint4 r4 = r4n;
         uint32_t k0 = 0, m1 = 0;
         if (RAND_DWELL) entry_kmers(entn, ent_sh, k0, m1);
@@ -648,11 +653,9 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned cha
 #ifdef SQG_KO_STORE
         if (pk.x == 0x12345678u && pk.y == 0x9abcdef0u) st_cs_v4(dst, pk);
         if (bad != 0) { n_redo++; w_redo = w; }
-        continue;
+        return;
 #endif
-        if (wb >= w_lo && wb + 32 <= w_hi) {   // (uniform) every chunk of this iteration lies wholly inside the tile
-            st_cs_v4(dst, pk);
-        } else if (w - w_lo < w_hi - w_lo) {
+        if (!EDGE || w - w_lo < w_hi - w_lo) {
             st_cs_v4(dst, pk);
         } else {
             // clipped chunk at an end of the tile (at most two per tile): store only the tile's own samples; the
@@ -665,7 +668,12 @@ __device__ __forceinline__ void emit_tile(const GenParams &p, const unsigned cha
             }
         }
         if (bad != 0) { n_redo++; w_redo = w; }
-    }
+    };
+    const uint32_t it_mid0 = (w_lo + 31) >> 5, it_mid1 = w_hi >> 5, it_end = (nW + 31) >> 5;   // clean iterations [it_mid0, it_mid1)
+    uint32_t it = 0;
+    for (; it < min(it_mid0, it_end); it++) iteration(32 * it, std::true_type{});
+    for (; it < it_mid1; it++) iteration(32 * it, std::false_type{});
+    for (; it < it_end; it++) iteration(32 * it, std::true_type{});
     if (__builtin_expect(n_redo != 0, 0)) {
         if (n_redo == 1) {
             exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, par_off, map_off, w_redo);
