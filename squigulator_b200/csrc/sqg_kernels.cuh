@@ -4,12 +4,12 @@
 //   a read is 1-2 SEGMENTS (the 2nd only for the RNA stall of --prefix, src/genread.c:88-89);
 //   a segment is cut into TILES of T consecutive k-mers; a tile is what one thread group turns into samples.
 //
-//   K0 tile_map_kernel     per segment: tile -> segment                                 -> tile_seg
-//   K1 dwell_sum_kernel    per tile: draw the T dwells (Philox), sum them              -> tile_sum
-//   K2 read_plan_kernel    per read: exclusive scan of its tile sums, per-read draws    -> tile_base, siglen, offset, median_before
-//   K3 read_offsets_kernel one CTA : exclusive scan of the 64-sample-aligned read lengths -> sigoff, totals
-//   K4 signal_kernel       per tile: encode k-mers, look up (mean,stdv), re-draw dwells, block scan,
-//                          then emit every int16 sample with 128-bit stores             -> signal  (the hot kernel)
+//   K0 tile_desc_kernel    per segment (warp): one 80-byte descriptor per tile                   -> tiles
+//   K1 dwell_kernel        per tile (warp)  : draw the T dwells (Philox + table normals)         -> dwells (u16), tile_sum, ss
+//   K2 read_plan_kernel    per read (warp)  : exclusive scan of its tile sums, per-read draws    -> tiles.B/S/L/offset, siglen, offset, median_before
+//   K3 read_offsets_kernel one CTA          : exclusive scan of the 64-sample-aligned lengths    -> sigoff, totals
+//   K4 signal_kernel       per tile (warp)  : encode k-mers, gather (mean,stdv), chunk map, then emit every int16
+//                          sample with 128-bit stores                                            -> signal  (the hot kernel)
 //
 // Reference statements: src/gensig.c:226-288 (gen_sig_core_seq), :293-343 (gen_sig_core), :346-356 (gen_sig).
 #pragma once
