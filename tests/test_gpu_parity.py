@@ -168,6 +168,40 @@ def test_ss_text(sq, oracle_lib):
         assert np.array_equal(y["svb"], H.oracle_svb_zd(oracle_lib, x["sig"]))
 
 
+def test_random_profiles(sq, oracle_lib, ztable):
+    """Seeded sweep over the parameter space the fixed cases do not visit: random ADC scaling, offsets (incl. signals
+    around zero and near the int16 limits), noise scales up to the wide-mode threshold and beyond, dwell laws from 1-2
+    samples per k-mer (many k-mers per 8-sample chunk) to hundreds (map capacity), every k, DNA and RNA order, prefix
+    junctions, IUPAC letters.  GPU == oracle bit for bit for each."""
+    rs = np.random.RandomState(20261017)
+    for it in range(60):
+        k = int(rs.choice([5, 6, 9]))
+        rna = bool(rs.randint(0, 2))
+        meth = (not rna) and k != 5 and rs.rand() < 0.2     # base-5 (CpG) model
+        flags = (H.SQ_RNA if rna else 0) | (H.SQ_R10 if k == 9 else 0)
+        if rs.rand() < 0.25:
+            flags |= H.SQ_PREFIX
+        if rs.rand() < 0.15:
+            flags |= int(rs.choice([H.SQ_IDEAL_TIME, H.SQ_IDEAL_AMP, H.SQ_IDEAL]))
+        dm = float(rs.choice([1.0, 2.0, 3.5, 9.0, 13.0, 31.0, 80.0, 400.0]))
+        ds = float(rs.choice([0.0, 0.5, 1.0, 4.0, 0.4 * dm]))
+        ds = min(ds, (1150.0 - dm) / 6.0)
+        dig = float(rs.choice([2048.0, 8192.0, 1024.0]))
+        rng_ = float(rs.uniform(150.0, 1500.0))
+        prof = dict(digitisation=dig, sample_rate=4000.0, bps=400.0, range=rng_,
+                    offset_mean=float(rs.choice([-250.0, 10.0, 900.0 * rng_ / dig * -1, 120.0 * dig / rng_])), offset_std=float(rs.uniform(0, 20)),
+                    median_before_mean=200.0, median_before_std=float(rs.uniform(0, 20)), dwell_mean=dm, dwell_std=ds)
+        amp = float(rs.choice([0.0, 0.3, 1.0, 1.0, 3.0, 40.0, 2000.0]))
+        alpha = b"ACGT" if rs.rand() < 0.7 else b"ACGTacgtNRYKMSWU"
+        if meth:
+            alpha = b"ACGTM" if rs.rand() < 0.7 else b"ACGTMacgtN"
+        n_reads = 6 if dm < 100 else 3
+        mean_len = int(rs.choice([30, 300, 2500])) if dm < 100 else 400
+        reads = H.random_reads(n_reads, mean_len, seed=int(rs.randint(1 << 30)), alphabet=alpha, min_len=0)
+        run_pair(sq, oracle_lib, ztable, prof, flags, k, reads, seed=int(rs.randint(1, 1 << 40)), amp_noise=amp,
+                 first=int(rs.randint(0, 1 << 35)), meth=meth)
+
+
 def test_batch_split_and_api_variants_agree(sq):
     """Output depends only on (seed, global read index, bases): not on batching, nor on which entry point is used."""
     reads = H.random_reads(24, 2500, seed=21, min_len=0)
