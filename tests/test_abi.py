@@ -89,3 +89,24 @@ def test_presets_match_compiled_reference_when_available():
         for fld in H.PROFILE_FIELDS:
             assert getattr(p, fld) == d[fld], (name, fld)
         assert H.PRESETS[name] == (d, flags)
+
+
+def build_c_demo(tmp_path):
+    """tests/c_abi_demo.c compiled as strict C99 against include/sqg.h and linked with libsqg.so"""
+    import squigulator_b200 as s
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(s.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_demo.c"), "-o", exe, "-L", libdir, "-lsqg", f"-Wl,-rpath,{libdir}"],
+                   check=True, capture_output=True)
+    return exe
+
+
+def test_header_is_c99_and_c_caller_fails_loudly_without_gpu(tmp_path):
+    """The reference is C99: its maintainer includes sqg.h from C.  Without a GPU the C caller gets SQG_ERR_NODEVICE."""
+    import torch
+    exe = build_c_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present (the run is checked by the gpu-marked test)")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and r.stdout.startswith("nodevice -6"), (r.returncode, r.stdout)

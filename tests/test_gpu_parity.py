@@ -202,6 +202,25 @@ def test_random_profiles(sq, oracle_lib, ztable):
                  first=int(rs.randint(0, 1 << 35)), meth=meth)
 
 
+def test_c_caller(sq, tmp_path):
+    """The boundary from plain C99 (tests/c_abi_demo.c): sqg_init, the gen_sig-shaped call, one batch with svb-zd and
+    ss:Z: text; its counts agree with the Python binding for the same read, model and seed."""
+    import subprocess
+    from tests.test_abi import build_c_demo
+    r = subprocess.run([build_c_demo(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), (r.returncode, r.stdout, r.stderr)
+    n_samples, n_kmers, svb_bytes, text_bytes = map(int, r.stdout.split()[1:5])
+    read = b"ACGTTGCATGCATGCAAACCCGGGTTTACGATCGATCGATTAGCTAGCTAGGATCGATCGGCTAGCTAGCATCGACTGACTAGCTAGCATCGATCGA"
+    model = np.empty(2 * 4096, dtype=np.float32)
+    model[0::2] = 60.0 + (np.arange(4096) % 70)
+    model[1::2] = 1.0 + (np.arange(4096) % 3)
+    gen = sq.SignalGenerator(dict(H.PRESETS["dna-r9-prom"][0]), model, 6, seed=1)
+    g = gen.gen_batch([read], want_ss=True)[0]
+    v = gen.gen_batch([read], want_svb=True, want_ss_text=True)[0]
+    gen.close()
+    assert (n_samples, n_kmers, svb_bytes, text_bytes) == (len(g["sig"]), len(g["ss"]), len(v["svb"]), len(v["ss_text"]))
+
+
 def test_batch_split_and_api_variants_agree(sq):
     """Output depends only on (seed, global read index, bases): not on batching, nor on which entry point is used."""
     reads = H.random_reads(24, 2500, seed=21, min_len=0)
