@@ -182,6 +182,7 @@ struct sqg_ctx {
     std::string err;
     DevBuf<float2> d_model;
     DevBuf<float4> d_pair_model;  // by (k+1)-mer: the parameters of both of its k-mers (base-4 models)
+    DevBuf<float4> d_quad_model;  // k <= 6: by (k+3)-mer, the parameters of its four k-mers (32-byte entries)
     DevBuf<unsigned char> d_z;  // Z32 ++ Z2
     GenParams base;     // configuration-derived part of the kernel parameters
     bool noisy = false, rand_dwell = false, meth = false, rev = false, prefix = false;
@@ -227,7 +228,7 @@ typedef void (*k4_fn)(const GenParams);
 template <int I>
 struct K4Table {
     static void fill(k4_fn *t) {
-        t[I] = (k4_fn)signal_kernel<(I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
+        t[I] = (k4_fn)signal_kernel<(I >> 4) & 1, (I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
         K4Table<I - 1>::fill(t);
     }
 };
@@ -236,15 +237,15 @@ struct K4Table<-1> {
     static void fill(k4_fn *) {}
 };
 
-// the 16 instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV>
-k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev) {
-    static k4_fn tab[16];
+// the instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV, QUAD> (QUAD: (k+3)-mer model gathers, k <= 6)
+k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev, bool quad) {
+    static k4_fn tab[32];
     static bool init = false;
     if (!init) {
-        K4Table<15>::fill(tab);
+        K4Table<31>::fill(tab);
         init = true;
     }
-    return tab[(noisy << 3) | (rnd << 2) | (meth << 1) | (int)rev];
+    return tab[(noisy << 4) | (rnd << 3) | (meth << 2) | (rev << 1) | (int)(quad && !meth)];
 }
 
 int slot_init(sqg_ctx *ctx, Slot &s) {
@@ -497,7 +498,7 @@ int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent
     if (ctx->legacy) return slot_generate_legacy(ctx, s);
     const GenParams p = slot_params(ctx, s);
     const int grid = (int)std::min<int64_t>((s.n_tiles + K4_WARPS - 1) / K4_WARPS, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->base.quad_model != nullptr);
     if (before) CU(cudaEventRecord(before, s.stream));
     void *args[] = {(void *)&p};
     CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(K4_THREADS), args, SM_TOTAL, s.stream));
@@ -758,6 +759,14 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
         ctx->base.pair_model = ctx->d_pair_model.p;
+        if (ctx->cfg.kmer_size <= 6 && ctx->cfg.kmer_size >= 1) {
+            const uint64_t n_quad = 64ull * n;   // 4^(k+3)
+            CU(ctx->d_quad_model.ensure((size_t)(2 * n_quad)));
+            quad_model_kernel<<<(unsigned)((n_quad + 255) / 256), 256>>>(ctx->d_model.p, ctx->d_quad_model.p, (uint32_t)n_quad, ctx->base.kmask);
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            ctx->base.quad_model = ctx->d_quad_model.p;
+        }
     }
     ctx->base.z32 = reinterpret_cast<const float *>(ctx->d_z.p);
     ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z32_BYTES);
@@ -787,7 +796,7 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     }
 
     CU(cudaFuncSetAttribute((const void *)dwell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->base.quad_model != nullptr);
     if (SM_TOTAL > prop.sharedMemPerBlockOptin) return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
     {
         // the sample loop addresses shared memory absolutely: dynamic array = reserved kilobyte + no static shared memory

@@ -65,6 +65,7 @@ struct GenParams {
     const ReadDesc *reads;
     const float2 *model;  // (level_mean, level_stdv) by rank
     const float4 *pair_model;  // by (k+1)-mer rank: the parameters of its two k-mers (first k bases, last k bases); base-4 models only
+    const float4 *quad_model;  // k <= 6: by (k+3)-mer rank, 32-byte entries: the parameters of its four k-mers (else NULL)
     const float *z32;     // Z32[32768]
     const float *z2;      // Z2[8192]
     // plan (written by K0-K3, read by K4)
@@ -126,6 +127,16 @@ __global__ void __launch_bounds__(256) pair_model_kernel(const float2 *__restric
     if (i >= n_pair) return;
     const float2 a = model[i >> 2], b = model[i & kmask];
     pair[i] = make_float4(a.x, a.y, b.x, b.y);
+}
+
+// k <= 6: the same idea one step further - a (k+3)-mer spans four consecutive k-mers, 4 x 8 bytes = exactly one 32-byte
+// sector, fetched with one 256-bit load (LDG.E.256); 4^(k+3) x 32 B = 8 MB for 6-mers.
+__global__ void __launch_bounds__(256) quad_model_kernel(const float2 *__restrict__ model, float4 *__restrict__ quad, uint32_t n_quad, uint32_t kmask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_quad) return;
+    const float2 a = model[(i >> 6) & kmask], b = model[(i >> 4) & kmask], c = model[(i >> 2) & kmask], d = model[i & kmask];
+    quad[2 * (size_t)i] = make_float4(a.x, a.y, b.x, b.y);
+    quad[2 * (size_t)i + 1] = make_float4(c.x, c.y, d.x, d.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -730,7 +741,7 @@ __device__ __forceinline__ void fetch_tile_desc(const GenParams &p, uint32_t wba
 }
 
 // Phase A of one tile.  Its descriptor, base window, dwells and arena offset are already in the warp's buffer.
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
 __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, unsigned char *smem, uint32_t par_off, uint32_t map_off,
                                                 uint32_t desc_off, uint32_t sigoff_off) {
     const TileDesc td = read_tile_desc(smem, desc_off);
@@ -827,6 +838,21 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
                            ((((dg[2] & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dg[3] & 0x03030303u) * 0x40100401u) >> 24);
         const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
         const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
+        if (QUAD) {
+            // k <= 6: two 256-bit gathers, each the four k-mers of one (k+3)-mer = one whole sector
+            const int shq = 26 - 2 * p.k;             // 32 - 2(k+3)
+            const uint32_t qmask = (p.kmask << 6) | 63u;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t r = (P >> (shq - 8 * h)) & qmask;
+                if (nk_tile < TK && m0 + 4 * h >= nk_tile) r = 0;
+                const float4 *src = p.quad_model + 2 * (size_t)r;
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(mv4[2 * h].x), "=f"(mv4[2 * h].y), "=f"(mv4[2 * h].z), "=f"(mv4[2 * h].w), "=f"(mv4[2 * h + 1].x),
+                               "=f"(mv4[2 * h + 1].y), "=f"(mv4[2 * h + 1].z), "=f"(mv4[2 * h + 1].w)
+                             : "l"(src));
+            }
+        } else
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             uint32_t r = (P >> (sh0 - 4 * ((j + rot4) & 3))) & pmask;
@@ -917,7 +943,8 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const float2 pa = make_par(mv4[j].x, mv4[j].y), pb = make_par(mv4[j].z, mv4[j].w);
-                    *reinterpret_cast<float4 *>(smem + par_off + 8 * (m0 + 2 * ((j + rot4) & 3))) = make_float4(pa.x, pa.y, pb.x, pb.y);
+                    const int piece = QUAD ? j : ((j + rot4) & 3);   // (the 256-bit gathers arrive in k-mer order)
+                    *reinterpret_cast<float4 *>(smem + par_off + 8 * (m0 + 2 * piece)) = make_float4(pa.x, pa.y, pb.x, pb.y);
                 }
             }
         } else {
@@ -952,7 +979,7 @@ __device__ __forceinline__ TileCtx prepare_tile(const GenParams &p, int lane, un
     return h;
 }
 
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
 __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
     constexpr bool USE_Z = NOISY;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -996,7 +1023,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
         cp_async_wait_all();
         __syncwarp();
         const uint32_t desc_off = map_off + W_DESC + slot * 80, sigoff_off = map_off + W_SIGOFF + slot * 8;
-        const TileCtx h = prepare_tile<NOISY, RAND_DWELL, METH, REV>(p, lane, smem, par_off, map_off, desc_off, sigoff_off);
+        const TileCtx h = prepare_tile<NOISY, RAND_DWELL, METH, REV, QUAD && !METH>(p, lane, smem, par_off, map_off, desc_off, sigoff_off);
         const int next = tile + stride;
         if (next < p.n_tiles) {
             fetch_tile_inputs<RAND_DWELL>(p, smem, wbase, map_off, map_off + W_DESC + (slot ^ 1) * 80, map_off + W_SIGOFF + (slot ^ 1) * 8, next, lane);
