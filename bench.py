@@ -173,7 +173,7 @@ def run_reference_arm(args, wl, rank):
                        "reads_per_step": reads_per_step},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,7 +302,24 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
     return out
 
 
+_JSON_FD = None
+
+
+def emit_json(line):
+    """The ONE line of stdout.  Everything else this process (or NCCL, or a child) writes to fd 1 goes to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)   # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)          # ... and send every other write to fd 1 (e.g. NCCL's version banner) to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -398,7 +415,7 @@ def main():
                 "clocks": res["clocks"], "e2e": res.get("e2e"), "e2e_svb": res.get("e2e_svb"), "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "cpu_baseline": cpu, "store_only_gbs": res["store_only_gbs"],
                 "wall_s_timed_region": res["wall_s"], "other_workloads": extra}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
