@@ -41,7 +41,7 @@ def synth_model(num_kmer, seed=7):
     return m
 
 
-def synth_reads(n_reads, mean_len, rna, seed, genome_mb=64):
+def synth_reads(n_reads, mean_len, rna, seed, genome_mb=64, with_coords=False):
     """Reads as the reference's sampler would cut them from a synthetic i.i.d. ACGT genome: length ~
     Gamma(2, rlen/2) (src/sim.c:243), uniform position, clipped at the contig end, <200 nt rejected
     (src/genread.c:125-154), strand coin + reverse complement.  RNA: whole 'transcripts' of ragged length
@@ -66,6 +66,12 @@ def synth_reads(n_reads, mean_len, rna, seed, genome_mb=64):
         if not rna and strand[i]:
             s = comp[s[::-1]]
         bases[off[i]:off[i + 1]] = lut[s]
+    if with_coords:  # the same reads as (contig, len, pos, strand) against the genome, for sqg_submit_coords
+        from squigulator_b200.api import COORD_DTYPE
+        co = np.zeros(len(lens), dtype=COORD_DTYPE)
+        co["len"], co["pos"] = lens, pos
+        co["strand"] = np.where((strand != 0) & (not rna), ord("-"), ord("+"))
+        return bases, off, lut[g], co
     return bases, off
 
 
@@ -181,7 +187,7 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
     import torch
     from squigulator_b200.api import PROFILES
     prof = PROFILES[wl["profile"]][0]
-    bases, off = synth_reads(reads_per_step, args.read_len, wl["rna"], seed=1000 + rank)
+    bases, off, genome, coords = synth_reads(reads_per_step, args.read_len, wl["rna"], seed=1000 + rank, with_coords=True)
     n_reads = len(off) - 1
     first = rank * n_reads  # read-index range of this GPU: the Philox counter makes the job independent of N
     out = {}
@@ -254,7 +260,7 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
         e_steps = max(6, min(steps, 24))
         checks = 0
 
-        def pipeline(n, want=0):
+        def pipeline(n, want=0, by_coords=False):
             nonlocal checks
             inflight, tot, d2h = [], 0, 0
 
@@ -271,7 +277,10 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
                 gen.release(t)
 
             for i in range(n):
-                inflight.append(gen.submit(hb, e_off, first_read_index=first, want=want))
+                if by_coords:
+                    inflight.append(gen.submit_coords(e_coords, first_read_index=first, want=want))
+                else:
+                    inflight.append(gen.submit(hb, e_off, first_read_index=first, want=want))
                 if len(inflight) == 3:
                     finish(inflight.pop(0))
             for t in inflight:
@@ -298,6 +307,21 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
         out["e2e_svb"] = {"value": sum_over_ranks(float(tot)) / dt, "unit": "samples/s",
                           "h2d_bytes_per_step": nb + (e_reads * 64), "d2h_bytes_per_step": d2h, "steps": e_steps,
                           "api": "same call with SQG_WANT_SVB: svb-zd streams (zig-zag delta + StreamVByte, bit-identical to slow5lib's) out"}
+        # both ends shrunk: reads named by coordinates against the genome resident in HBM, svb-zd out
+        gen.load_genome([genome.tobytes()])
+        e_coords = np.ascontiguousarray(coords[:e_reads])
+        tot0 = tot
+        pipeline(3, want=2, by_coords=True)
+        barrier()
+        t0 = time.perf_counter()
+        tot, d2h = pipeline(e_steps, want=2, by_coords=True)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert tot == tot0, "coordinate batches must generate exactly the reads of the host-bases batches"
+        out["e2e_coords_svb"] = {"value": sum_over_ranks(float(tot)) / dt, "unit": "samples/s",
+                                 "h2d_bytes_per_step": e_reads * (24 + 8), "d2h_bytes_per_step": d2h, "steps": e_steps,
+                                 "api": "sqg_submit_coords with SQG_WANT_SVB: 24-byte coordinates in, reads cut out of the "
+                                        "HBM-resident genome on the GPU, svb-zd streams out"}
         lib.sqg_host_free(hp)
     return out
 
@@ -412,7 +436,7 @@ def main():
                            "samples_per_step_per_gpu": res["samples_per_step_per_gpu"],
                            "l2": "output per step (GBs) far exceeds the 126 MB L2; no flush needed",
                            "rng": "philox4x32-7", "parallelism": f"reads sharded over {world} GPU(s), no hot-path collective"},
-                "clocks": res["clocks"], "e2e": res.get("e2e"), "e2e_svb": res.get("e2e_svb"), "gpu_launches": res["gpu_launches"],
+                "clocks": res["clocks"], "e2e": res.get("e2e"), "e2e_svb": res.get("e2e_svb"), "e2e_coords_svb": res.get("e2e_coords_svb"), "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "cpu_baseline": cpu, "store_only_gbs": res["store_only_gbs"],
                 "wall_s_timed_region": res["wall_s"], "other_workloads": extra}
         emit_json(line)

@@ -125,6 +125,9 @@ typedef struct {
     const int64_t *svb_len;        /* n_reads */
     const char *ss_text;           /* SQG_WANT_SS_TEXT: read i's dwell string = ss_text[ss_text_off[i] .. ss_text_off[i+1]) */
     const int64_t *ss_text_off;    /* n_reads+1 */
+    const char *bases;             /* SQG_WANT_BASES (coordinate batches): read i = bases[bases_off[i] .. bases_off[i+1]) */
+    const int64_t *bases_off;      /* n_reads+1 */
+    int64_t meth_draws;            /* coordinate batches with meth: rand_meth draws this batch consumed */
 } sqg_result_t;
 
 /* bases: the reads' characters back to back (no terminators needed); read i = bases[base_off[i] ..
@@ -143,6 +146,40 @@ int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t
                int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket);
 int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res);
 int sqg_release(sqg_ctx_t *ctx, sqg_ticket_t ticket);
+
+/* ---- device-resident genome: reads named by coordinates, extracted on the GPU ----
+ * Replaces, for accepted reads, the sequence work of gen_read() (src/genread.c:357): the copy out of the reference
+ * (gen_read_common, src/genread.c:149-153), the replacement of every 'N' by the read's own minstd stream seeded 100
+ * (is_bad_read, src/genread.c:132-140), reverse_complement() for '-' reads (src/seq.h:77-112) and the CpG -> 'M'
+ * marking of methylate_dna() (src/genread.c:207-241).  Coordinate SAMPLING and the accept/reject decision stay with
+ * the caller (they consume the reference's ref_pos/strand/rlen streams in host order); so does the contig-end clip:
+ * pos + len must lie inside the contig.
+ *
+ * seq: all contigs back to back, contig c = seq[contig_off[c] .. contig_off[c+1]) (ASCII, as load_ref() holds them:
+ * case, N and IUPAC letters keep the reference's meaning).  meth: NULL, or one uint8 per base with the same indexing
+ * (ref->ref_meth, src/ref.c:346); contig_has_meth: NULL (= all, when meth != NULL) or one flag per contig
+ * (ref->ref_meth[c] != NULL).  Copied to HBM once; the host arrays are not retained.  Calling it again replaces the genome. */
+int sqg_genome_load(sqg_ctx_t *ctx, int32_t n_contigs, const char *seq, const int64_t *contig_off,
+                    const uint8_t *meth, const uint8_t *contig_has_meth);
+
+typedef struct {
+    int32_t contig; /* index into the loaded genome */
+    int32_t len;    /* *rlen of gen_read: bases in the read, >= 0 */
+    int64_t pos;    /* *ref_pos: 0-based start on the forward strand */
+    int32_t strand; /* '+' or '-' (src/genread.c:196-200) */
+    int32_t reserved;
+} sqg_coord_t;
+
+#define SQG_WANT_BASES 0x8u /* coordinate batches: also return the extracted reads (for FASTA/FASTQ/SAM records) */
+
+/* As sqg_gen_batch / sqg_submit, the reads given as coordinates.  meth_draw_base = number of values already taken
+ * from the reference's rand_meth stream (seed + 6, src/sim.c:230-246; thread 0) before this batch: with cfg->meth the
+ * j-th CpG site of the batch (read order, then position order) uses draw meth_draw_base + j, exactly the value
+ * `squigulator -t1` would use; res->meth_draws tells the caller how far the batch advanced the stream. */
+int sqg_gen_batch_coords(sqg_ctx_t *ctx, int64_t n_reads, const sqg_coord_t *coords, int64_t first_read_index,
+                         int64_t meth_draw_base, uint32_t want, sqg_result_t *res);
+int sqg_submit_coords(sqg_ctx_t *ctx, int64_t n_reads, const sqg_coord_t *coords, int64_t first_read_index,
+                      int64_t meth_draw_base, uint32_t want, sqg_ticket_t *ticket);
 
 /* ---- per-read drop-in with gen_sig's own shape (src/gensig.c:346) ----
  * Returns a malloc()'d buffer the caller free()s (slow5lib free()s rec->raw_signal itself,

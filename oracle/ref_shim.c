@@ -204,3 +204,46 @@ int64_t sqref_svb_zd(const int16_t *sig, int64_t n, uint8_t *out, int64_t cap) {
     free(p);
     return (int64_t)bytes;
 }
+
+/* ---- gen_read() (src/genread.c:357) over an in-memory genome, for pinning the read-extraction restatement.
+ * Contig c = seq[off[c] .. off[c+1]); meth (nullable) has the same indexing.  The strings are copied. ---- */
+int sqref_set_genome(void *hv, int n, const char *seq, const int64_t *off, const uint8_t *meth) {
+    core_t *core = ((sqref_t *)hv)->core;
+    ref_t *ref = (ref_t *)calloc(1, sizeof(ref_t));
+    ref->num_ref = n;
+    ref->ref_names = (char **)calloc(n, sizeof(char *));
+    ref->ref_seq = (char **)calloc(n, sizeof(char *));
+    ref->ref_lengths = (int32_t *)calloc(n, sizeof(int32_t));
+    ref->ref_meth = meth ? (uint8_t **)calloc(n, sizeof(uint8_t *)) : NULL;
+    for (int c = 0; c < n; c++) {
+        int64_t len = off[c + 1] - off[c];
+        char name[32];
+        snprintf(name, sizeof name, "ctg%d", c);
+        ref->ref_names[c] = strdup(name);
+        ref->ref_seq[c] = strndup(seq + off[c], len);
+        ref->ref_lengths[c] = (int32_t)len;
+        ref->sum += len;
+        if (meth) {
+            ref->ref_meth[c] = (uint8_t *)malloc(len ? len : 1);
+            memcpy(ref->ref_meth[c], meth + off[c], len);
+        }
+    }
+    core->ref = ref;
+    return 0;
+}
+
+/* one accepted read from thread 0's streams.  Returns rlen (the read is copied to buf, cap >= rlen), or -1. */
+int32_t sqref_gen_read(void *hv, int32_t *contig, int32_t *ref_pos, char *strand, char *buf, int32_t cap) {
+    core_t *core = ((sqref_t *)hv)->core;
+    char *rid = NULL;
+    int32_t ref_len = 0, rlen = 0;
+    int8_t rna = core->opt.flag & SQ_RNA ? 1 : 0;
+    char *seq = gen_read(core, &rid, &ref_len, ref_pos, &rlen, strand, rna, 0);
+    if (!seq || rlen > cap) { free(seq); return -1; }
+    memcpy(buf, seq, rlen);
+    free(seq);
+    *contig = -1;
+    for (int c = 0; c < core->ref->num_ref; c++)
+        if (core->ref->ref_names[c] == rid) *contig = c;
+    return rlen;
+}

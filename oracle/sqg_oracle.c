@@ -503,3 +503,56 @@ int64_t sqo_ss_text(const int32_t *ss, int64_t n, int rna, char *out) {
     }
     return (int64_t)(p - out);
 }
+
+/* ------------------------------------------------------------------ read extraction */
+
+static uint64_t mulmod31(uint64_t a, uint64_t b) { return (a * b) % 2147483647ULL; }
+
+int64_t sqo_lehmer_jump(int64_t seed, uint64_t n) {
+    /* one Schrage step maps any state x to 16807*x mod m (up to the sign convention of the stored value), so n steps
+     * give seed*16807^n mod m; 0 stands for m */
+    uint64_t r = (uint64_t)(seed % 2147483647LL + 2147483647LL) % 2147483647ULL, a = 16807, e = n, pw = 1;
+    while (e) {
+        if (e & 1) pw = mulmod31(pw, a);
+        a = mulmod31(a, a);
+        e >>= 1;
+    }
+    r = mulmod31(r, pw);
+    return (int64_t)(r ? r : (n ? 2147483647ULL : 0));
+}
+
+int64_t sqo_extract_read(const char *contig, int64_t contig_len, const uint8_t *contig_meth, int64_t pos, int32_t len,
+                         char strand, int64_t *meth_state, char *out) {
+    /* src/genread.c:149-153 (the caller has clipped len at the contig end) + :132-140 */
+    int64_t nstate = 100;
+    for (int32_t i = 0; i < len; i++) {
+        char b = contig[pos + i];
+        if (b == 'N') {
+            int n = (int)round(sqo_lehmer_next(&nstate) * 3);
+            b = n == 0 ? 'A' : n == 1 ? 'C' : n == 2 ? 'G' : 'T';
+        }
+        out[i] = b;
+    }
+    if (strand == '-') { /* src/seq.h:77-112 */
+        for (int32_t i = 0, j = len - 1; i <= j; i++, j--) {
+            char x = out[i], y = out[j], cx, cy;
+            cx = (x == 'A' || x == 'a') ? 'T' : (x == 'C' || x == 'c') ? 'G' : (x == 'G' || x == 'g') ? 'C'
+                 : (x == 'T' || x == 't') ? 'A' : 'T';
+            cy = (y == 'A' || y == 'a') ? 'T' : (y == 'C' || y == 'c') ? 'G' : (y == 'G' || y == 'g') ? 'C'
+                 : (y == 'T' || y == 't') ? 'A' : 'T';
+            out[i] = cy;
+            out[j] = cx;
+        }
+    }
+    int64_t draws = 0;
+    if (meth_state && contig_meth) { /* src/genread.c:207-241 */
+        for (int32_t i = 0; i < len; i++) {
+            if (pos + i + 1 < contig_len && i + 1 < len && contig[pos + i] == 'C' && contig[pos + i + 1] == 'G') {
+                int methr = (int)(sqo_lehmer_next(meth_state) * 254);
+                draws++;
+                if (methr <= contig_meth[pos + i]) out[strand == '-' ? len - i - 2 : i] = 'M';
+            }
+        }
+    }
+    return draws;
+}

@@ -78,6 +78,16 @@ float sqo_fma_rz(float x, float y, float z);            /* PTX fma.rz.f32, resta
 int64_t sqo_ss_text(const int32_t *ss, int64_t n, int rna, char *out);     /* src/format.c:69-75 */
 int64_t sqo_svb_zd_encode(const int16_t *sig, int64_t n, uint8_t *out); /* slow5lib/src/slow5_press.c:1055-1087 */
 
+/* the sequence work gen_read() does for an ACCEPTED read (src/genread.c:149-153 copy, :132-140 N replacement,
+ * src/seq.h:77-112 reverse complement, src/genread.c:207-241 CpG marking).  contig/contig_meth: one contig
+ * (contig_meth NULL = no methylation data); *meth_state: the rand_meth stream (src/sim.c:253), advanced as the
+ * reference would (NULL = no marking).  out: len bytes.  Returns the number of rand_meth draws taken. */
+int64_t sqo_extract_read(const char *contig, int64_t contig_len, const uint8_t *contig_meth, int64_t pos, int32_t len,
+                         char strand, int64_t *meth_state, char *out);
+/* state of a minstd stream after n draws from `seed` (seed*16807^n mod 2^31-1), as a value sqo_lehmer_next continues
+ * from; holds for 0 <= seed <= 2^31-1 (a larger seed leaves the modular form for its first few draws) */
+int64_t sqo_lehmer_jump(int64_t seed, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ SQ_RNA, SQ_FULL_CONTIG, SQ_IDEAL, SQ_IDEAL_TIME, SQ_IDEAL_AMP, SQ_PREFIX, SQ_R10
 RNG_PHILOX, RNG_LEGACY = 0, 1
 WANT_SS = 0x1
 WANT_SVB = 0x2
+WANT_BASES = 0x8
 WANT_SS_TEXT = 0x4
 
 PROFILE_FIELDS = ("digitisation", "sample_rate", "bps", "range", "offset_mean", "offset_std",
@@ -59,7 +60,13 @@ class Result(C.Structure):
                 ("offset", C.POINTER(C.c_double)), ("median_before", C.POINTER(C.c_double)),
                 ("ss", C.POINTER(C.c_int32)), ("ss_off", C.POINTER(C.c_int64)),
                 ("svb", C.POINTER(C.c_uint8)), ("svb_off", C.POINTER(C.c_int64)), ("svb_len", C.POINTER(C.c_int64)),
-                ("ss_text", C.POINTER(C.c_char)), ("ss_text_off", C.POINTER(C.c_int64))]
+                ("ss_text", C.POINTER(C.c_char)), ("ss_text_off", C.POINTER(C.c_int64)),
+                ("bases", C.POINTER(C.c_char)), ("bases_off", C.POINTER(C.c_int64)), ("meth_draws", C.c_int64)]
+
+
+# == sqg_coord_t, as a numpy record (one row per read)
+COORD_DTYPE = np.dtype([("contig", np.int32), ("len", np.int32), ("pos", np.int64), ("strand", np.int32),
+                        ("reserved", np.int32)])
 
 
 class SqgError(RuntimeError):
@@ -79,6 +86,9 @@ _SIGNATURES = {
     "sqg_host_free": (None, [C.c_void_p]),
     "sqg_gen_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.POINTER(Result)]),
     "sqg_submit": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.POINTER(C.c_int64)]),
+    "sqg_genome_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqg_gen_batch_coords": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.POINTER(Result)]),
+    "sqg_submit_coords": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.POINTER(C.c_int64)]),
     "sqg_wait": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Result)]),
     "sqg_release": (C.c_int, [C.c_void_p, C.c_int64]),
     "sqg_gen_sig": (C.POINTER(C.c_int16), [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -174,6 +184,9 @@ class SignalGenerator:
         if res.ss_text:  # SQG_WANT_SS_TEXT: the PAF/SAM `ss:Z:` value of every read
             to = np.ctypeslib.as_array(res.ss_text_off, shape=(n + 1,))
             txt = C.string_at(res.ss_text, int(to[-1]))
+        if res.bases:  # SQG_WANT_BASES (coordinate batches): the reads the GPU cut out of the genome
+            bo = np.ctypeslib.as_array(res.bases_off, shape=(n + 1,))
+            bases = C.string_at(res.bases, int(bo[-1]))
         out = []
         for i in range(n):
             d = dict(offset=float(o[i]), median_before=float(mb[i]), n_samples=int(ln[i]))
@@ -186,6 +199,8 @@ class SignalGenerator:
                 d["svb"] = svb[vo[i]:vo[i] + vl[i]].copy()
             if ss is not None:
                 d["ss"] = ss[so[i]:so[i + 1]].copy()
+            if res.bases:
+                d["bases"] = bases[bo[i]:bo[i + 1]]
             out.append(d)
         return out
 
@@ -204,6 +219,41 @@ class SignalGenerator:
         self._check(self.lib.sqg_gen_batch(self.h, len(off) - 1, bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
                                            first_read_index, want, C.byref(res)))
         return res
+
+    # -- device-resident genome, reads by coordinates (what gen_read does for accepted reads, src/genread.c:357)
+    def load_genome(self, contigs, meth=None, contig_has_meth=None):
+        """contigs: list of bytes; meth: None or list of uint8 arrays (one per contig, same lengths)"""
+        seq, off = _pack_reads(contigs)
+        m = None
+        if meth is not None:
+            m = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8) for x in meth]))
+            assert m.size == seq.size
+        f = None if contig_has_meth is None else np.ascontiguousarray(contig_has_meth, dtype=np.uint8)
+        self._check(self.lib.sqg_genome_load(self.h, len(contigs), seq.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                             None if m is None else m.ctypes.data_as(C.c_void_p),
+                                             None if f is None else f.ctypes.data_as(C.c_void_p)))
+
+    @staticmethod
+    def pack_coords(coords):
+        """coords: iterable of (contig, pos, len, strand) with strand '+' or '-'"""
+        a = np.zeros(len(coords), dtype=COORD_DTYPE)
+        for i, (c, pos, ln, st) in enumerate(coords):
+            a[i] = (c, ln, pos, ord(st), 0)
+        return a
+
+    def gen_batch_coords(self, coords, first_read_index=0, meth_draw_base=0, want=0):
+        """returns (per-read dicts, rand_meth draws the batch consumed)"""
+        a = coords if isinstance(coords, np.ndarray) else self.pack_coords(coords)
+        res = Result()
+        self._check(self.lib.sqg_gen_batch_coords(self.h, len(a), a.ctypes.data_as(C.c_void_p) if len(a) else None,
+                                                  first_read_index, meth_draw_base, want, C.byref(res)))
+        return self._unpack(res), int(res.meth_draws)
+
+    def submit_coords(self, coords, first_read_index=0, meth_draw_base=0, want=0):
+        t = C.c_int64()
+        self._check(self.lib.sqg_submit_coords(self.h, len(coords), coords.ctypes.data_as(C.c_void_p), first_read_index,
+                                               meth_draw_base, want, C.byref(t)))
+        return t.value
 
     # -- async dispatcher
     def submit(self, bases, off, first_read_index=0, want=0):

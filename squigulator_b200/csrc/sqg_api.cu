@@ -29,6 +29,7 @@
 #include "sqg_legacy.cuh"
 #include "sqg_svb.cuh"
 #include "sqg_sstext.cuh"
+#include "sqg_extract.cuh"
 
 extern "C" const unsigned char sqg_ztable_blob[];  // Z32 ++ Z2 (binary32), embedded from data/ztable_v3.bin (ztable_blob.S)
 
@@ -121,6 +122,16 @@ struct Slot {
     PinBuf<int64_t> h_sst_off;
     PinBuf<char> h_sst;
     int64_t sst_bytes = 0;
+    // coordinate batches (sqg_extract.cuh)
+    DevBuf<Coord> d_coords;
+    DevBuf<int64_t> d_out_off;
+    DevBuf<uint64_t> d_cg_count, d_cg_off;
+    DevBuf<unsigned char> d_scan_tmp;
+    PinBuf<int64_t> h_base_off;
+    PinBuf<uint64_t> h_cg;
+    PinBuf<char> h_bases;
+    bool from_coords = false;
+    int64_t meth_draws = 0;
     // SQG_RNG_LEGACY scratch (per k-mer of the batch)
     DevBuf<uint32_t> d_rank, d_rank_sorted, d_idx, d_idx_sorted;
     DevBuf<uint64_t> d_dsorted, d_excl, d_heads, d_segstart, d_cpos;
@@ -148,6 +159,8 @@ struct Slot {
         h_ss.release();
         d_svb_len.release(); d_svb_off.release(); d_svb.release(); h_svb_len.release(); h_svb_off.release(); h_svb.release();
         d_sst_len.release(); d_sst_off.release(); d_ss_off.release(); d_sst.release(); h_sst_off.release(); h_sst.release();
+        d_coords.release(); d_out_off.release(); d_cg_count.release(); d_cg_off.release(); d_scan_tmp.release();
+        h_base_off.release(); h_cg.release(); h_bases.release();
         for (auto e : kev) cudaEventDestroy(e);
         kev.clear();
         if (ev0) cudaEventDestroy(ev0);
@@ -166,6 +179,8 @@ struct Job {
     int64_t first_read;
     uint32_t want;
     int status = 1;  // 1 = running, <=0 = done with that code
+    const sqg_coord_t *coords = nullptr;  // coordinate batch (bases/base_off unused)
+    int64_t meth_draw_base = 0;
 };
 
 }  // namespace
@@ -184,6 +199,11 @@ struct sqg_ctx {
     DevBuf<float4> d_pair_model;  // by (k+1)-mer: the parameters of both of its k-mers (base-4 models)
     DevBuf<float4> d_quad_model;  // k <= 6: by (k+3)-mer, the parameters of its four k-mers (32-byte entries)
     DevBuf<unsigned char> d_z;  // Z32 ++ Z2
+    // device-resident genome (sqg_genome_load)
+    DevBuf<uint8_t> d_genome, d_gmeth, d_has_meth;
+    DevBuf<int64_t> d_contig_off;
+    std::vector<int64_t> contig_off;
+    bool genome_meth = false, genome_has_flags = false;
     GenParams base;     // configuration-derived part of the kernel parameters
     bool noisy = false, rand_dwell = false, meth = false, rev = false, prefix = false;
     int k4_grid_per_sm = 1;
@@ -257,10 +277,37 @@ int slot_init(sqg_ctx *ctx, Slot &s) {
 
 // ---- host-side batch preparation: reads -> segments -> tiles (replaces the per-read bookkeeping at the
 // top of gen_sig_core / gen_sig_core_seq, src/gensig.c:240-245, :302-309, and attach_prefix) ----
+int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_draw_base);
+
 int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, const int64_t *base_off,
-                 int64_t first_read, uint32_t want) {
-    if (n_reads < 0 || (n_reads > 0 && (!bases || !base_off))) return fail(ctx, SQG_ERR_ARG, "null input");
+                 int64_t first_read, uint32_t want, const sqg_coord_t *coords = nullptr, int64_t meth_draw_base = 0) {
+    if (n_reads < 0) return fail(ctx, SQG_ERR_ARG, "negative read count");
     if (n_reads > 0x3FFFFFFF) return fail(ctx, SQG_ERR_ARG, "too many reads in one batch");
+    s.from_coords = coords != nullptr;
+    s.meth_draws = 0;
+    if (coords) {  // lengths come with the coordinates; the bases are cut out on the device (slot_extract)
+        if (ctx->contig_off.empty()) return fail(ctx, SQG_ERR_STATE, "no genome loaded (sqg_genome_load)");
+        if (meth_draw_base < 0) return fail(ctx, SQG_ERR_ARG, "negative meth_draw_base");
+        if (ctx->meth && ctx->genome_meth && (ctx->cfg.seed + 6 < 0 || ctx->cfg.seed + 6 > 2147483647))
+            return fail(ctx, SQG_ERR_ARG, "CpG marking needs 0 <= seed + 6 <= 2^31-1 (minstd stream seed + 6, src/sim.c:253; "
+                                          "larger seeds leave the stream's modular form for its first draws)");
+        CU(s.h_base_off.ensure((size_t)n_reads + 1));
+        const int64_t nc = (int64_t)ctx->contig_off.size() - 1;
+        int64_t acc = 0;
+        for (int64_t r = 0; r < n_reads; r++) {
+            const sqg_coord_t &c = coords[r];
+            if (c.contig < 0 || c.contig >= nc || c.len < 0 || c.pos < 0 ||
+                c.pos + c.len > ctx->contig_off[c.contig + 1] - ctx->contig_off[c.contig])
+                return fail(ctx, SQG_ERR_ARG, "read coordinates outside the loaded genome");
+            if (c.strand != '+' && c.strand != '-') return fail(ctx, SQG_ERR_ARG, "strand must be '+' or '-'");
+            s.h_base_off.p[r] = acc;
+            acc += c.len;
+        }
+        s.h_base_off.p[n_reads] = acc;
+        base_off = s.h_base_off.p;
+    } else if (n_reads > 0 && (!bases || !base_off)) {
+        return fail(ctx, SQG_ERR_ARG, "null input");
+    }
     const int k = (int)ctx->cfg.kmer_size;
     const int T = ctx->base.T;
     const bool prefix = ctx->prefix, rna = ctx->rev;
@@ -349,8 +396,12 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
         CU(cudaStreamSynchronize(s.stream));  // c is a stack buffer
         s.const_written = true;
     }
-    if (total_bases)
+    if (coords) {
+        int rc = slot_extract(ctx, s, coords, meth_draw_base);
+        if (rc != SQG_OK) return rc;
+    } else if (total_bases) {
         CU(cudaMemcpyAsync(s.d_bases.p + CONST_REGION, bases + user0, (size_t)total_bases, cudaMemcpyHostToDevice, s.stream));
+    }
     CU(s.d_segs.ensure((size_t)std::max<int64_t>(nseg, 1), false, s.stream));
     CU(s.d_reads.ensure((size_t)std::max<int64_t>(n_reads, 1), false, s.stream));
     if (nseg) CU(cudaMemcpyAsync(s.d_segs.p, s.h_segs.p, (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s.stream));
@@ -367,6 +418,53 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     CU(s.d_meta.ensure(4, false, s.stream));
     CU(s.h_meta.ensure(4));
     if ((want & (SQG_WANT_SS | SQG_WANT_SS_TEXT)) || ctx->legacy) CU(s.d_ss.ensure((size_t)std::max<int64_t>(nk_total, 1), false, s.stream));
+    return SQG_OK;
+}
+
+// coordinate batches: the reads' bases are written into d_bases by the extraction kernels (sqg_extract.cuh)
+int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_draw_base) {
+    const size_t n = (size_t)s.n_reads;
+    CU(s.h_cg.ensure(2));
+    s.h_cg.p[0] = s.h_cg.p[1] = 0;
+    if (!n) return SQG_OK;
+    static_assert(sizeof(Coord) == sizeof(sqg_coord_t), "Coord mirrors sqg_coord_t");
+    CU(s.d_coords.ensure(n, false, s.stream));
+    CU(s.d_out_off.ensure(n + 1, false, s.stream));
+    CU(cudaMemcpyAsync(s.d_coords.p, coords, n * sizeof(Coord), cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_out_off.p, s.h_base_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+    ExtractParams q;
+    memset(&q, 0, sizeof q);
+    q.genome = ctx->d_genome.p;
+    q.contig_off = ctx->d_contig_off.p;
+    q.meth = ctx->genome_meth ? ctx->d_gmeth.p : nullptr;
+    q.contig_has_meth = ctx->genome_has_flags ? ctx->d_has_meth.p : nullptr;
+    q.coords = s.d_coords.p;
+    q.out_off = s.d_out_off.p;
+    q.out = s.d_bases.p + CONST_REGION;
+    q.n_reads = (int32_t)n;
+    q.do_meth = ctx->meth && ctx->genome_meth;
+    q.meth_residue = seed_residue(ctx->cfg.seed + 6);  // rand_meth of thread 0, src/sim.c:253
+    q.meth_draw_base = (uint64_t)meth_draw_base;
+    q.pw[0] = 1;
+    for (int j = 1; j <= 32; j++) q.pw[j] = mulmod31(q.pw[j - 1], LEHMER_A);
+    const int grid = (int)((n + EX_THREADS / 32 - 1) / (EX_THREADS / 32));
+    if (q.do_meth) {
+        CU(s.d_cg_count.ensure(n, false, s.stream));
+        CU(s.d_cg_off.ensure(n, false, s.stream));
+        q.cg_count = s.d_cg_count.p;
+        q.cg_off = s.d_cg_off.p;
+        extract_count_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
+        size_t tmp = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, q.cg_count, q.cg_off, (int)n, s.stream));
+        CU(s.d_scan_tmp.ensure(tmp + 16, false, s.stream));
+        CU(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp, q.cg_count, q.cg_off, (int)n, s.stream));
+        CU(cudaMemcpyAsync(&s.h_cg.p[0], q.cg_off + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(&s.h_cg.p[1], q.cg_count + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        ctx->launches += 2;
+    }
+    extract_reads_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
     return SQG_OK;
 }
 
@@ -564,6 +662,28 @@ int slot_sstext(sqg_ctx *ctx, Slot &s) {
     return SQG_OK;
 }
 
+void fill_result(Slot &s, sqg_result_t *res) {
+    const bool svb = (s.want & SQG_WANT_SVB) != 0;
+    const bool want_bases = s.from_coords && (s.want & SQG_WANT_BASES);
+    res->n_reads = s.n_reads;
+    res->total_samples = s.total_samples;
+    res->signal = svb ? nullptr : s.h_sig.p;
+    res->sig_off = s.h_sigoff.p;
+    res->len_raw_signal = s.h_len64.p;
+    res->offset = s.h_offset.p;
+    res->median_before = s.h_median.p;
+    res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
+    res->ss_off = s.h_ss_off.p;
+    res->svb = svb ? s.h_svb.p : nullptr;
+    res->svb_off = svb ? s.h_svb_off.p : nullptr;
+    res->svb_len = svb ? s.h_svb_len.p : nullptr;
+    res->ss_text = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst.p : nullptr;
+    res->ss_text_off = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst_off.p : nullptr;
+    res->bases = want_bases ? s.h_bases.p : nullptr;
+    res->bases_off = want_bases ? s.h_base_off.p : nullptr;
+    res->meth_draws = s.from_coords ? s.meth_draws : 0;
+}
+
 // D2H of everything the caller gets back; fills *res.  Synchronises the slot's stream.
 int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     const size_t n = (size_t)s.n_reads;
@@ -597,31 +717,24 @@ int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
             CU(cudaMemcpyAsync(s.h_ss.p, s.d_ss.p, (size_t)s.total_kmers * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         }
     }
+    const bool want_bases = s.from_coords && (s.want & SQG_WANT_BASES);
+    if (want_bases) {
+        CU(s.h_bases.ensure((size_t)std::max<int64_t>(s.total_bases, 1)));
+        if (s.total_bases)
+            CU(cudaMemcpyAsync(s.h_bases.p, s.d_bases.p + CONST_REGION, (size_t)s.total_bases, cudaMemcpyDeviceToHost, s.stream));
+    }
     CU(cudaStreamSynchronize(s.stream));
     for (size_t i = 0; i < n; i++) s.h_len64.p[i] = (int64_t)s.h_siglen.p[i];
-    if (res) {
-        res->n_reads = s.n_reads;
-        res->total_samples = s.total_samples;
-        res->signal = svb ? nullptr : s.h_sig.p;
-        res->sig_off = s.h_sigoff.p;
-        res->len_raw_signal = s.h_len64.p;
-        res->offset = s.h_offset.p;
-        res->median_before = s.h_median.p;
-        res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
-        res->ss_off = s.h_ss_off.p;
-        res->svb = svb ? s.h_svb.p : nullptr;
-        res->svb_off = svb ? s.h_svb_off.p : nullptr;
-        res->svb_len = svb ? s.h_svb_len.p : nullptr;
-        res->ss_text = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst.p : nullptr;
-        res->ss_text_off = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst_off.p : nullptr;
-    }
+    if (s.from_coords) s.meth_draws = (int64_t)(s.h_cg.p[0] + s.h_cg.p[1]);
+    if (res) fill_result(s, res);
     return SQG_OK;
 }
 
 int slot_run_all(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, const int64_t *base_off,
-                 int64_t first_read, uint32_t want, sqg_result_t *res) {
+                 int64_t first_read, uint32_t want, sqg_result_t *res, const sqg_coord_t *coords = nullptr,
+                 int64_t meth_draw_base = 0) {
     int rc;
-    if ((rc = slot_prepare(ctx, s, n_reads, bases, base_off, first_read, want)) != SQG_OK) return rc;
+    if ((rc = slot_prepare(ctx, s, n_reads, bases, base_off, first_read, want, coords, meth_draw_base)) != SQG_OK) return rc;
     if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
     if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
     if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
@@ -643,7 +756,7 @@ void worker_main(sqg_ctx *ctx, int slot_idx) {
         }
         // NB: ctx->err is shared; jobs report through their status code
         int rc = slot_run_all(ctx, ctx->slots[slot_idx], job->n_reads, job->bases, job->base_off, job->first_read,
-                              job->want, nullptr);
+                              job->want, nullptr, job->coords, job->meth_draw_base);
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
             job->status = rc;
@@ -881,6 +994,7 @@ void sqg_destroy(sqg_ctx_t *ctx) {
     ctx->d_model.release();
     ctx->d_z.release();
     ctx->d_cnt_kmer.release();
+    ctx->d_genome.release(); ctx->d_gmeth.release(); ctx->d_has_meth.release(); ctx->d_contig_off.release();
     delete ctx;
 }
 
@@ -901,8 +1015,9 @@ int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int6
     return slot_run_all(ctx, ctx->sync_slot, n_reads, bases, base_off, first_read_index, want, res);
 }
 
-int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
-               int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket) {
+static int submit_job(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                      const sqg_coord_t *coords, int64_t meth_draw_base, int64_t first_read_index, uint32_t want,
+                      sqg_ticket_t *ticket) {
     if (!ctx || !ticket) return SQG_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_dispatcher(ctx);
@@ -914,13 +1029,69 @@ int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t
             if (!ctx->slot_busy[i]) { slot = (int)i; return true; }
         return false;
     });
-    Job *job = new Job{ctx->next_ticket++, slot, n_reads, bases, base_off, first_read_index, want, 1};
+    Job *job = new Job{ctx->next_ticket++, slot, n_reads, bases, base_off, first_read_index, want, 1, coords, meth_draw_base};
     ctx->slot_busy[slot] = 1;
     ctx->jobs[job->ticket] = job;
     ctx->queues[slot].push_back(job);
     *ticket = job->ticket;
     lk.unlock();
     ctx->cv_work.notify_all();
+    return SQG_OK;
+}
+
+int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+               int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket) {
+    return submit_job(ctx, n_reads, bases, base_off, nullptr, 0, first_read_index, want, ticket);
+}
+
+int sqg_submit_coords(sqg_ctx_t *ctx, int64_t n_reads, const sqg_coord_t *coords, int64_t first_read_index,
+                      int64_t meth_draw_base, uint32_t want, sqg_ticket_t *ticket) {
+    if (n_reads > 0 && !coords) return ctx ? fail(ctx, SQG_ERR_ARG, "null coordinates") : SQG_ERR_ARG;
+    static const sqg_coord_t none = {0, 0, 0, '+', 0};
+    return submit_job(ctx, n_reads, nullptr, nullptr, coords ? coords : &none, meth_draw_base, first_read_index, want, ticket);
+}
+
+int sqg_gen_batch_coords(sqg_ctx_t *ctx, int64_t n_reads, const sqg_coord_t *coords, int64_t first_read_index,
+                         int64_t meth_draw_base, uint32_t want, sqg_result_t *res) {
+    if (!ctx || !res) return SQG_ERR_ARG;
+    if (n_reads > 0 && !coords) return fail(ctx, SQG_ERR_ARG, "null coordinates");
+    static const sqg_coord_t none = {0, 0, 0, '+', 0};
+    CU(cudaSetDevice(ctx->device));
+    return slot_run_all(ctx, ctx->sync_slot, n_reads, nullptr, nullptr, first_read_index, want, res,
+                        coords ? coords : &none, meth_draw_base);
+}
+
+int sqg_genome_load(sqg_ctx_t *ctx, int32_t n_contigs, const char *seq, const int64_t *contig_off,
+                    const uint8_t *meth, const uint8_t *contig_has_meth) {
+    if (!ctx) return SQG_ERR_ARG;
+    if (n_contigs < 1 || !seq || !contig_off) return fail(ctx, SQG_ERR_ARG, "genome: need >= 1 contig, seq and contig_off");
+    for (int32_t c = 0; c < n_contigs; c++)
+        if (contig_off[c + 1] < contig_off[c]) return fail(ctx, SQG_ERR_ARG, "genome: contig_off must be non-decreasing");
+    if (contig_off[0] != 0) return fail(ctx, SQG_ERR_ARG, "genome: contig_off[0] must be 0");
+    CU(cudaSetDevice(ctx->device));
+    {  // no batch may be in flight while the genome is replaced
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        for (int b : ctx->slot_busy)
+            if (b) return fail(ctx, SQG_ERR_STATE, "genome load while batches are in flight");
+    }
+    const size_t total = (size_t)contig_off[n_contigs];
+    CU(cudaDeviceSynchronize());
+    CU(ctx->d_genome.ensure(total + 64));
+    CU(ctx->d_contig_off.ensure((size_t)n_contigs + 1));
+    CU(cudaMemcpy(ctx->d_genome.p, seq, total, cudaMemcpyHostToDevice));
+    CU(cudaMemset(ctx->d_genome.p + total, 0, 64));
+    CU(cudaMemcpy(ctx->d_contig_off.p, contig_off, ((size_t)n_contigs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    ctx->genome_meth = meth != nullptr;
+    ctx->genome_has_flags = meth != nullptr && contig_has_meth != nullptr;
+    if (meth) {
+        CU(ctx->d_gmeth.ensure(total + 64));
+        CU(cudaMemcpy(ctx->d_gmeth.p, meth, total, cudaMemcpyHostToDevice));
+        if (contig_has_meth) {
+            CU(ctx->d_has_meth.ensure((size_t)n_contigs));
+            CU(cudaMemcpy(ctx->d_has_meth.p, contig_has_meth, (size_t)n_contigs, cudaMemcpyHostToDevice));
+        }
+    }
+    ctx->contig_off.assign(contig_off, contig_off + n_contigs + 1);
     return SQG_OK;
 }
 
@@ -932,24 +1103,7 @@ int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res) {
     Job *job = it->second;
     ctx->cv_done.wait(lk, [&] { return job->status <= 0; });
     if (job->status != SQG_OK) return job->status;
-    if (res) {
-        Slot &s = ctx->slots[job->slot];
-        res->n_reads = s.n_reads;
-        res->total_samples = s.total_samples;
-        const bool svb = (s.want & SQG_WANT_SVB) != 0;
-        res->signal = svb ? nullptr : s.h_sig.p;
-        res->sig_off = s.h_sigoff.p;
-        res->len_raw_signal = s.h_len64.p;
-        res->offset = s.h_offset.p;
-        res->median_before = s.h_median.p;
-        res->ss = (s.want & SQG_WANT_SS) ? s.h_ss.p : nullptr;
-        res->ss_off = s.h_ss_off.p;
-        res->svb = svb ? s.h_svb.p : nullptr;
-        res->svb_off = svb ? s.h_svb_off.p : nullptr;
-        res->svb_len = svb ? s.h_svb_len.p : nullptr;
-        res->ss_text = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst.p : nullptr;
-        res->ss_text_off = (s.want & SQG_WANT_SS_TEXT) ? s.h_sst_off.p : nullptr;
-    }
+    if (res) fill_result(ctx->slots[job->slot], res);
     return SQG_OK;
 }
 

@@ -75,6 +75,11 @@ def load_oracle():
     lib.sqo_kmer_rank.argtypes = [C.c_char_p, C.c_uint32]
     lib.sqo_meth_kmer_rank.restype = C.c_uint32
     lib.sqo_meth_kmer_rank.argtypes = [C.c_char_p, C.c_uint32]
+    lib.sqo_extract_read.restype = C.c_int64
+    lib.sqo_extract_read.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_char,
+                                     C.POINTER(C.c_int64), C.c_void_p]
+    lib.sqo_lehmer_jump.restype = C.c_int64
+    lib.sqo_lehmer_jump.argtypes = [C.c_int64, C.c_uint64]
     lib.sqo_lehmer_next.restype = C.c_double
     lib.sqo_lehmer_next.argtypes = [C.POINTER(C.c_int64)]
     lib.sqo_lehmer_normal.restype = C.c_double
@@ -220,3 +225,34 @@ def oracle_ss_text(lib, ss, rna):
     out = np.empty(12 * ss.size + 16, dtype=np.uint8)
     n = lib.sqo_ss_text(ss.ctypes.data_as(C.c_void_p), ss.size, int(bool(rna)), out.ctypes.data_as(C.c_void_p))
     return out[:n].tobytes()
+
+
+def oracle_extract_read(lib, contig, meth, pos, length, strand, meth_state=None):
+    """what gen_read() hands to gen_sig for an accepted read (oracle restatement of src/genread.c / src/seq.h).
+    meth_state: None, or a ctypes c_int64 holding the rand_meth stream (advanced in place).
+    Returns (read bytes, rand_meth draws taken)."""
+    out = C.create_string_buffer(max(length, 1))
+    m = None if meth is None else np.ascontiguousarray(meth, dtype=np.uint8)
+    n = lib.sqo_extract_read(contig, len(contig), None if m is None else m.ctypes.data_as(C.c_void_p), pos, length,
+                             strand.encode() if isinstance(strand, str) else strand,
+                             C.byref(meth_state) if meth_state is not None else None, out)
+    return out.raw[:length], int(n)
+
+
+def synthetic_genome(seed=11, n_contigs=3, mean_len=3000, with_meth=True):
+    """small contigs with everything the extraction has to get right: N runs, lower case, IUPAC letters, CpGs"""
+    rs = np.random.RandomState(seed)
+    contigs, meth = [], []
+    for c in range(n_contigs):
+        ln = int(mean_len * (0.6 + 0.8 * rs.rand()))
+        a = np.frombuffer(b"ACGT", dtype=np.uint8)[rs.randint(0, 4, ln)].copy()
+        for _ in range(3):  # N runs and single Ns
+            p0 = rs.randint(0, ln - 40)
+            a[p0:p0 + rs.randint(1, 30)] = ord("N")
+        a[rs.randint(0, ln, 12)] = ord("N")
+        lo = rs.randint(0, ln - 200)
+        a[lo:lo + 150] |= 0x20  # a soft-masked stretch (lower case; an 'n' there is NOT replaced)
+        a[rs.randint(0, ln, 6)] = np.frombuffer(b"RYKMSW", dtype=np.uint8)
+        contigs.append(a.tobytes())
+        meth.append(rs.randint(0, 256, ln).astype(np.uint8))
+    return contigs, (meth if with_meth else None)

@@ -1,0 +1,193 @@
+"""Reads named by coordinates: the sequence work of the reference's gen_read() for accepted reads —
+copy, 'N' replacement, reverse complement, CpG -> 'M' marking (src/genread.c:125-281, src/seq.h:77-112).
+
+CPU: the oracle's restatement against golden vectors made from the UNMODIFIED reference (tests/golden/gen_read.json,
+scripts/make_golden_reads.py) and, where oracle/_ref is built, against the reference itself on fresh draws.
+GPU: sqg_gen_batch_coords against the oracle, byte for byte, and its signal against the host-bases path."""
+import ctypes as C
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+SO = os.path.join(H.ROOT, "oracle", "_ref", "libsqref.so")
+
+
+@pytest.fixture(scope="module")
+def oracle_lib():
+    return H.load_oracle()
+
+
+def meth_state_for(seed):
+    return C.c_int64(seed + 6)  # rand_meth of thread 0, src/sim.c:253
+
+
+def check_against(oracle_lib, reads, contigs, marr, seed, meth):
+    """reads: (contig, pos, len, strand, expected bytes or sha256 hex); returns total rand_meth draws"""
+    st = meth_state_for(seed) if meth else None
+    total = 0
+    for i, (c, pos, ln, strand, want) in enumerate(reads):
+        got, draws = H.oracle_extract_read(oracle_lib, contigs[c], marr[c] if meth else None, pos, ln, strand, st)
+        total += draws
+        if isinstance(want, bytes):
+            assert got == want, f"read {i}: {(c, pos, ln, strand)}"
+        else:
+            assert hashlib.sha256(got).hexdigest() == want, f"read {i}: {(c, pos, ln, strand)}"
+    return total
+
+
+def test_oracle_equals_golden_reads(oracle_lib):
+    doc = json.load(open(os.path.join(H.GOLDEN_DIR, "gen_read.json")))
+    assert len(doc) == 3
+    for case in doc:
+        contigs, marr = H.synthetic_genome(seed=case["genome_seed"], with_meth=True)
+        assert hashlib.sha256(b"".join(contigs)).hexdigest() == case["genome_sha256"]
+        reads = [(r["contig"], r["pos"], r["len"], r["strand"], r["sha256"]) for r in case["reads"]]
+        draws = check_against(oracle_lib, reads, contigs, marr, case["seed"], case["meth"])
+        if case["meth"]:
+            assert draws > 1000  # the marking really ran (and stayed in step over 60 reads: one slip breaks every later read)
+        assert {r["strand"] for r in case["reads"]} == ({"+"} if case["name"].startswith("rna") else {"+", "-"})
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/libsqref.so not built")
+@pytest.mark.parametrize("preset,seed,meth", [("dna-r10-prom", 5, True), ("dna-r9-prom", 99, False), ("rna-r9-prom", 17, False)])
+def test_oracle_equals_reference_gen_read(oracle_lib, preset, seed, meth):
+    sys.path.insert(0, os.path.join(H.ROOT, "scripts"))
+    import make_golden_reads as G
+    contigs, marr = H.synthetic_genome(seed=seed + 100, n_contigs=4, mean_len=2500)
+    reads = G.reference_reads(G.load_ref(), preset, seed, meth, contigs, marr, 80)
+    check_against(oracle_lib, reads, contigs, marr, seed, meth)
+
+
+def test_lehmer_jump(oracle_lib):
+    for seed in (0, 1, 7, 48, 127773, 2147483646, 2147483647):
+        st = C.c_int64(seed)
+        seq = [oracle_lib.sqo_lehmer_next(C.byref(st)) for _ in range(300)]
+        for n in (0, 1, 2, 31, 32, 33, 255, 298):
+            j = C.c_int64(oracle_lib.sqo_lehmer_jump(seed, n))
+            assert oracle_lib.sqo_lehmer_next(C.byref(j)) == seq[n], (seed, n)
+
+
+def test_extraction_edge_cases(oracle_lib):
+    ctg = b"NNCGNACGTnCGCGN"
+    m = np.full(len(ctg), 255, dtype=np.uint8)
+    # whole contig, forward: every upper-case N replaced from the stream seeded 100; both sites after position 0 marked
+    st = C.c_int64(1 + 6)
+    got, draws = H.oracle_extract_read(oracle_lib, ctg, m, 0, len(ctg), "+", st)
+    assert len(got) == len(ctg) and b"N" not in got and got[9:10] == b"n"
+    assert draws == ctg.count(b"CG") == 4 and got.count(b"M") == 4
+    # a site cut by the read's end is not a site (i+1 < rlen, src/genread.c:211)
+    got, draws = H.oracle_extract_read(oracle_lib, ctg, m, 0, 3, "+", C.c_int64(7))
+    assert draws == 0 and got[2:3] == b"C"
+    # reverse strand: M lands on the complement of the G
+    got, draws = H.oracle_extract_read(oracle_lib, b"AACGTT", np.full(6, 255, np.uint8), 0, 6, "-", C.c_int64(7))
+    assert got == b"AAMGTT" and draws == 1
+    # empty read
+    got, draws = H.oracle_extract_read(oracle_lib, ctg, m, 4, 0, "-", C.c_int64(7))
+    assert got == b"" and draws == 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+
+def _coords(contigs, n, seed, min_len=1):
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        c = int(rs.randint(0, len(contigs)))
+        L = len(contigs[c])
+        ln = int(min(L, max(min_len, rs.gamma(2.0, 400))))
+        pos = int(rs.randint(0, L - ln + 1))
+        out.append((c, pos, ln, "+-"[int(rs.randint(0, 2))]))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("meth", [False, True])
+def test_coords_batch_equals_oracle_and_host_path(oracle_lib, meth):
+    import squigulator_b200 as sq
+    from squigulator_b200 import api
+    k = 6
+    nk = (5 if meth else 4) ** k
+    model = H.random_model(nk, seed=5)
+    seed = 21
+    contigs, marr = H.synthetic_genome(seed=31, n_contigs=5, mean_len=4000)
+    coords = _coords(contigs, 300, seed=8) + [(0, 0, len(contigs[0]), "-"), (1, 5, 0, "+"), (2, len(contigs[2]) - 1, 1, "-"),
+                                              (3, 0, 33, "+"), (3, 1, 32, "-"), (4, 7, 31, "-")]
+    g = sq.SignalGenerator("dna-r9-prom", model, k, seed=seed, meth=meth)
+    g.load_genome(contigs, meth=marr)
+    out, draws = g.gen_batch_coords(coords, first_read_index=1000, want=api.WANT_BASES | api.WANT_SS)
+    # bytes == oracle, read by read, the rand_meth stream running across the batch
+    st = meth_state_for(seed) if meth else None
+    total = 0
+    for i, (c, pos, ln, strand) in enumerate(coords):
+        want, d = H.oracle_extract_read(oracle_lib, contigs[c], marr[c] if meth else None, pos, ln, strand, st)
+        total += d
+        assert out[i]["bases"] == want, f"read {i}: {coords[i]}"
+    assert draws == total and (total > 500 if meth else total == 0)
+    # the signal is what the host-bases path gives for those reads
+    ref = g.gen_batch([o["bases"] for o in out], first_read_index=1000, want_ss=True)
+    for a, b in zip(out, ref):
+        np.testing.assert_array_equal(a["sig"], b["sig"])
+        np.testing.assert_array_equal(a["ss"], b["ss"])
+        assert a["offset"] == b["offset"]
+    # two batches chained by meth_draws == one batch (addressable draws)
+    h1, d1 = g.gen_batch_coords(coords[:117], first_read_index=1000, meth_draw_base=0, want=api.WANT_BASES)
+    h2, d2 = g.gen_batch_coords(coords[117:], first_read_index=1117, meth_draw_base=d1, want=api.WANT_BASES)
+    assert d1 + d2 == draws
+    for a, b in zip(h1 + h2, out):
+        assert a["bases"] == b["bases"]
+        np.testing.assert_array_equal(a["sig"], b["sig"])
+    # asynchronous submission gives the same
+    arr = g.pack_coords(coords)
+    t = g.submit_coords(arr, first_read_index=1000, meth_draw_base=0, want=api.WANT_BASES)
+    res = g.wait(t)
+    got = g._unpack(res)
+    assert int(res.meth_draws) == draws
+    for a, b in zip(got, out):
+        assert a["bases"] == b["bases"]
+        np.testing.assert_array_equal(a["sig"], b["sig"])
+    g.release(t)
+    g.close()
+
+
+@pytest.mark.gpu
+def test_coords_golden_reads_through_gpu():
+    """the reference's own gen_read() output (golden) out of the GPU extraction, RNA included"""
+    import squigulator_b200 as sq
+    from squigulator_b200 import api
+    doc = json.load(open(os.path.join(H.GOLDEN_DIR, "gen_read.json")))
+    for case in doc:
+        contigs, marr = H.synthetic_genome(seed=case["genome_seed"], with_meth=True)
+        meth = case["meth"]
+        k = 5
+        g = sq.SignalGenerator(case["preset"], H.random_model((5 if meth else 4) ** k, seed=2), k, seed=case["seed"], meth=meth)
+        g.load_genome(contigs, meth=marr if meth else None)
+        coords = [(r["contig"], r["pos"], r["len"], r["strand"]) for r in case["reads"]]
+        out, _ = g.gen_batch_coords(coords, want=api.WANT_BASES)
+        for o, r in zip(out, case["reads"]):
+            assert hashlib.sha256(o["bases"]).hexdigest() == r["sha256"]
+        g.close()
+
+
+@pytest.mark.gpu
+def test_coords_errors():
+    import squigulator_b200 as sq
+    g = sq.SignalGenerator("dna-r9-prom", H.random_model(4 ** 6), 6)
+    with pytest.raises(sq.SqgError) as e:
+        g.gen_batch_coords([(0, 0, 10, "+")])
+    assert e.value.code == -5  # SQG_ERR_STATE: no genome
+    g.load_genome([b"ACGT" * 50, b"GGCC" * 10])
+    for bad in [(2, 0, 10, "+"), (0, 195, 10, "+"), (1, -1, 4, "+"), (0, 0, -1, "-"), (0, 0, 10, "x")]:
+        with pytest.raises(sq.SqgError) as e:
+            g.gen_batch_coords([bad])
+        assert e.value.code == -1, bad
+    out, d = g.gen_batch_coords([])
+    assert out == [] and d == 0
+    out, d = g.gen_batch_coords([(1, 36, 4, "-")], want=0x8)
+    assert out[0]["bases"] == b"GGCC" and d == 0
+    g.close()
