@@ -124,6 +124,8 @@ struct Slot {
     int64_t sst_bytes = 0;
     // coordinate batches (sqg_extract.cuh)
     DevBuf<Coord> d_coords;
+    DevBuf<PieceRef> d_pieces;
+    PinBuf<PieceRef> h_pieces;
     DevBuf<int64_t> d_out_off;
     DevBuf<uint64_t> d_cg_count, d_cg_off;
     DevBuf<unsigned char> d_scan_tmp;
@@ -159,6 +161,7 @@ struct Slot {
         h_ss.release();
         d_svb_len.release(); d_svb_off.release(); d_svb.release(); h_svb_len.release(); h_svb_off.release(); h_svb.release();
         d_sst_len.release(); d_sst_off.release(); d_ss_off.release(); d_sst.release(); h_sst_off.release(); h_sst.release();
+        d_pieces.release(); h_pieces.release();
         d_coords.release(); d_out_off.release(); d_cg_count.release(); d_cg_off.release(); d_scan_tmp.release();
         h_base_off.release(); h_cg.release(); h_bases.release();
         for (auto e : kev) cudaEventDestroy(e);
@@ -426,12 +429,25 @@ int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_
     const size_t n = (size_t)s.n_reads;
     CU(s.h_cg.ensure(2));
     s.h_cg.p[0] = s.h_cg.p[1] = 0;
-    if (!n) return SQG_OK;
+    if (!n || !s.total_bases) return SQG_OK;
+    if (s.total_bases > 0xFFFFFFFFll) return fail(ctx, SQG_ERR_ARG, "coordinate batch too large (>= 2^32 bases)");
     static_assert(sizeof(Coord) == sizeof(sqg_coord_t), "Coord mirrors sqg_coord_t");
+    // pieces of XSEG positions, one warp each
+    size_t np = 0;
+    for (size_t r = 0; r < n; r++) np += ((size_t)coords[r].len + XSEG - 1) / XSEG;
+    CU(s.h_pieces.ensure(np));
+    np = 0;
+    for (size_t r = 0; r < n; r++)
+        for (int32_t k = 0; (int64_t)k * XSEG < coords[r].len; k++) s.h_pieces.p[np++] = PieceRef{(int32_t)r, k};
+    if (np > 0x7FFFFFF0) return fail(ctx, SQG_ERR_ARG, "coordinate batch too large (piece count)");
     CU(s.d_coords.ensure(n, false, s.stream));
     CU(s.d_out_off.ensure(n + 1, false, s.stream));
+    CU(s.d_pieces.ensure(np, false, s.stream));
+    CU(s.d_cg_count.ensure(np, false, s.stream));
+    CU(s.d_cg_off.ensure(np, false, s.stream));
     CU(cudaMemcpyAsync(s.d_coords.p, coords, n * sizeof(Coord), cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.d_out_off.p, s.h_base_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_pieces.p, s.h_pieces.p, np * sizeof(PieceRef), cudaMemcpyHostToDevice, s.stream));
     ExtractParams q;
     memset(&q, 0, sizeof q);
     q.genome = ctx->d_genome.p;
@@ -439,31 +455,27 @@ int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_
     q.meth = ctx->genome_meth ? ctx->d_gmeth.p : nullptr;
     q.contig_has_meth = ctx->genome_has_flags ? ctx->d_has_meth.p : nullptr;
     q.coords = s.d_coords.p;
+    q.pieces = s.d_pieces.p;
     q.out_off = s.d_out_off.p;
     q.out = s.d_bases.p + CONST_REGION;
-    q.n_reads = (int32_t)n;
+    q.cnt = s.d_cg_count.p;
+    q.cnt_off = s.d_cg_off.p;
+    q.n_pieces = (int32_t)np;
     q.do_meth = ctx->meth && ctx->genome_meth;
     q.meth_residue = seed_residue(ctx->cfg.seed + 6);  // rand_meth of thread 0, src/sim.c:253
     q.meth_draw_base = (uint64_t)meth_draw_base;
     q.pw[0] = 1;
     for (int j = 1; j <= 32; j++) q.pw[j] = mulmod31(q.pw[j - 1], LEHMER_A);
-    const int grid = (int)((n + EX_THREADS / 32 - 1) / (EX_THREADS / 32));
-    if (q.do_meth) {
-        CU(s.d_cg_count.ensure(n, false, s.stream));
-        CU(s.d_cg_off.ensure(n, false, s.stream));
-        q.cg_count = s.d_cg_count.p;
-        q.cg_off = s.d_cg_off.p;
-        extract_count_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
-        size_t tmp = 0;
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, q.cg_count, q.cg_off, (int)n, s.stream));
-        CU(s.d_scan_tmp.ensure(tmp + 16, false, s.stream));
-        CU(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp, q.cg_count, q.cg_off, (int)n, s.stream));
-        CU(cudaMemcpyAsync(&s.h_cg.p[0], q.cg_off + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(&s.h_cg.p[1], q.cg_count + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
-        ctx->launches += 2;
-    }
+    const int grid = (int)((np + EX_THREADS / 32 - 1) / (EX_THREADS / 32));
+    extract_count_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, q.cnt, q.cnt_off, (int)np, s.stream));
+    CU(s.d_scan_tmp.ensure(tmp + 16, false, s.stream));
+    CU(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp, q.cnt, q.cnt_off, (int)np, s.stream));
+    CU(cudaMemcpyAsync(&s.h_cg.p[0], q.cnt_off + (np - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(&s.h_cg.p[1], q.cnt + (np - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
     extract_reads_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
-    ctx->launches += 1;
+    ctx->launches += 3;
     CU(cudaGetLastError());
     return SQG_OK;
 }
@@ -725,7 +737,7 @@ int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     }
     CU(cudaStreamSynchronize(s.stream));
     for (size_t i = 0; i < n; i++) s.h_len64.p[i] = (int64_t)s.h_siglen.p[i];
-    if (s.from_coords) s.meth_draws = (int64_t)(s.h_cg.p[0] + s.h_cg.p[1]);
+    if (s.from_coords) s.meth_draws = (int64_t)((s.h_cg.p[0] + s.h_cg.p[1]) & 0xFFFFFFFFull);  // low half: CpG sites
     if (res) fill_result(s, res);
     return SQG_OK;
 }

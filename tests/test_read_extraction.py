@@ -118,6 +118,9 @@ def test_coords_batch_equals_oracle_and_host_path(oracle_lib, meth):
     contigs, marr = H.synthetic_genome(seed=31, n_contigs=5, mean_len=4000)
     coords = _coords(contigs, 300, seed=8) + [(0, 0, len(contigs[0]), "-"), (1, 5, 0, "+"), (2, len(contigs[2]) - 1, 1, "-"),
                                               (3, 0, 33, "+"), (3, 1, 32, "-"), (4, 7, 31, "-")]
+    # whole contigs and piece-boundary lengths on both strands (reads are cut into 2048-position pieces on the GPU)
+    coords += [(c, 0, len(contigs[c]), st) for c in range(5) for st in "+-"]
+    coords += [(c, 3, ln, st) for c in (0, 2) for ln in (2047, 2048, 2049, 2176) for st in "+-" if ln + 3 <= len(contigs[c])]
     g = sq.SignalGenerator("dna-r9-prom", model, k, seed=seed, meth=meth)
     g.load_genome(contigs, meth=marr)
     out, draws = g.gen_batch_coords(coords, first_read_index=1000, want=api.WANT_BASES | api.WANT_SS)
