@@ -2,17 +2,20 @@
  *
  * Plain-C, single-threaded restatement of the reference hot path
  * (/root/reference src/gensig.c:226-356, src/seq.h:14-74, src/rand.h:79-94, src/sim.c:215-258,
- *  src/genread.c:37-123).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ *  src/genread.c:37-281).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this; nothing under squigulator_b200/ links or imports it.
  *
  * Two random-number modes:
  *   SQO_RNG_LEGACY  the reference's own minstd/Lehmer streams + libm Box-Muller, stream-for-stream
  *                   (pinned bit-exactly against the reference's golden .exp files and against
  *                   oracle/_ref/libsqref.so, see tests/test_oracle_golden.py)
- *   SQO_RNG_PHILOX  the counter-based scheme the CUDA path implements (DESIGN.md "Philox mode"):
- *                   Philox4x32-10 keyed by the seed, counters (block, read_lo, read_hi, stream),
- *                   16-bit uniforms -> standard normal through the shared quantile table.
+ *   SQO_RNG_PHILOX  the counter-based scheme the CUDA path implements:
+ *                   Philox4x32-7 keyed by the seed, counters (block, read_lo, read_hi, stream), eight
+ *                   10-bit draws per block -> standard normal through the class-stratified quantile
+ *                   table (squigulator_b200/data/ztable_v3.bin), samples by fma.rz in binary32.
  *                   The GPU must equal this bit for bit.
+ * Also restated here, each pinned to the compiled reference: slow5lib's svb-zd stream, the PAF/SAM
+ * ss:Z: text (src/format.c:69-75) and the sequence work of gen_read() (src/genread.c, src/seq.h).
  */
 #ifndef SQG_ORACLE_H
 #define SQG_ORACLE_H
