@@ -472,10 +472,11 @@ int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, q.cnt, q.cnt_off, (int)np, s.stream));
     CU(s.d_scan_tmp.ensure(tmp + 16, false, s.stream));
     CU(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp, q.cnt, q.cnt_off, (int)np, s.stream));
-    CU(cudaMemcpyAsync(&s.h_cg.p[0], q.cnt_off + (np - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaMemcpyAsync(&s.h_cg.p[1], q.cnt + (np - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+    publish_kernel<<<1, 32, 0, s.stream>>>(reinterpret_cast<const int64_t *>(q.cnt_off + (np - 1)), 1,
+                                           reinterpret_cast<const int64_t *>(q.cnt + (np - 1)), 1,
+                                           reinterpret_cast<int64_t *>(s.h_cg.p));
     extract_reads_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
-    ctx->launches += 3;
+    ctx->launches += 4;
     CU(cudaGetLastError());
     return SQG_OK;
 }
@@ -545,7 +546,8 @@ int slot_plan(sqg_ctx *ctx, Slot &s) {
 // read the totals back (one small D2H + sync) and make sure the signal arena is large enough
 int slot_size_arena(sqg_ctx *ctx, Slot &s) {
     if (s.n_reads == 0) { s.arena_need = s.total_samples = 0; return SQG_OK; }
-    CU(cudaMemcpyAsync(s.h_meta.p, s.d_meta.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    publish_kernel<<<1, 32, 0, s.stream>>>(s.d_meta.p, 4, nullptr, 0, s.h_meta.p);  // not a D2H copy: see publish_kernel
+    ctx->launches += 1;
     CU(cudaStreamSynchronize(s.stream));
     if (s.h_meta.p[2]) return fail(ctx, SQG_ERR_RANGE, "a read has >= UINT32_MAX samples (reference: src/sim.c:559-562)");
     s.arena_need = s.h_meta.p[0];
@@ -635,7 +637,8 @@ int slot_compress(sqg_ctx *ctx, Slot &s) {
     q.svb_len = s.d_svb_len.p; q.svb_off = s.d_svb_off.p; q.svb = nullptr; q.n_reads = (int32_t)s.n_reads;
     svb_size_kernel<<<(int)s.n_reads, SVB_THREADS, 0, s.stream>>>(q);
     svb_offsets_kernel<<<1, 1024, 0, s.stream>>>(q);
-    CU(cudaMemcpyAsync(s.h_svb_off.p + n, s.d_svb_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    publish_kernel<<<1, 32, 0, s.stream>>>(s.d_svb_off.p + n, 1, nullptr, 0, s.h_svb_off.p + n);
+    ctx->launches += 1;
     CU(cudaStreamSynchronize(s.stream));
     s.svb_bytes = s.h_svb_off.p[n];
     CU(s.d_svb.ensure((size_t)std::max<int64_t>(s.svb_bytes, 16), false, s.stream));
@@ -661,7 +664,7 @@ int slot_sstext(sqg_ctx *ctx, Slot &s) {
     q.n_reads = (int32_t)s.n_reads; q.reversed = ctx->rev ? 1 : 0;
     sstext_size_kernel<<<(int)s.n_reads, SST_THREADS, 0, s.stream>>>(q);
     sstext_offsets_kernel<<<1, 1024, 0, s.stream>>>(q);
-    CU(cudaMemcpyAsync(s.h_sst_off.p, s.d_sst_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    publish_kernel<<<1, 32, 0, s.stream>>>(s.d_sst_off.p + n, 1, nullptr, 0, s.h_sst_off.p + n);
     CU(cudaStreamSynchronize(s.stream));
     s.sst_bytes = s.h_sst_off.p[n];
     CU(s.d_sst.ensure((size_t)std::max<int64_t>(s.sst_bytes, 16), false, s.stream));
@@ -669,7 +672,8 @@ int slot_sstext(sqg_ctx *ctx, Slot &s) {
     q.text = s.d_sst.p;
     sstext_write_kernel<<<(int)s.n_reads, SST_THREADS, 0, s.stream>>>(q);
     CU(cudaMemcpyAsync(s.h_sst.p, s.d_sst.p, (size_t)s.sst_bytes, cudaMemcpyDeviceToHost, s.stream));
-    ctx->launches += 3;
+    CU(cudaMemcpyAsync(s.h_sst_off.p, s.d_sst_off.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    ctx->launches += 4;
     CU(cudaGetLastError());
     return SQG_OK;
 }

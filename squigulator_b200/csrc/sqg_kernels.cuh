@@ -1051,6 +1051,15 @@ __global__ void __launch_bounds__(256) prefix_shift_kernel(const __grid_constant
     for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) out[i] = (int16_t)(out[i] - (int16_t)p.shift_val);
 }
 
+// A few 64-bit values from device memory straight into PINNED HOST memory (unified addressing: the host pointer is valid
+// on the device).  Used for the per-batch totals the host has to see before it can size buffers: a cudaMemcpyAsync of
+// 8 bytes would queue on the D2H copy engine behind another slot's gigabyte of signal and stall this slot's kernels.
+__global__ void publish_kernel(const int64_t *a, int na, const int64_t *b, int nb, int64_t *host_dst) {
+    const int t = threadIdx.x;
+    if (t < na) host_dst[t] = a[t];
+    else if (t < na + nb) host_dst[t] = b[t - na];
+}
+
 // store-only kernel: the HBM write ceiling next to which the signal kernel is read
 __global__ void __launch_bounds__(512) store_only_kernel(uint4 *dst, size_t n16) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
