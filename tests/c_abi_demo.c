@@ -1,6 +1,6 @@
 /* tests/c_abi_demo.c — the drop-in boundary used from plain C99, as a maintainer of the reference would:
  * sqg_init with a profile_t-shaped struct and a model_t-shaped table, one gen_sig-shaped call, one batch call with
- * svb-zd and ss:Z: text output.  Prints "nodevice <code>" and exits 3 when there is no GPU (no CPU fallback), else
+ * svb-zd and ss:Z: text output, one batch of reads named by coordinates against a GPU-resident genome.  Prints "nodevice <code>" and exits 3 when there is no GPU (no CPU fallback), else
  * "ok <samples> <kmers> <svb bytes> <text bytes>".  Built and run by tests/test_abi.py and tests/test_gpu_parity.py. */
 #include <stdio.h>
 #include <stdlib.h>
@@ -47,7 +47,32 @@ int main(void) {
     uint32_t n0;
     memcpy(&n0, r.svb + r.svb_off[0], 4);
     if ((int64_t)n0 != len) { printf("svb header %u\n", n0); return 9; }
-    printf("ok %lld %lld %lld %lld\n", (long long)len, (long long)ss_n, (long long)r.svb_len[0], (long long)(r.ss_text_off[1] - r.ss_text_off[0]));
+    const int64_t svb_bytes = r.svb_len[0], text_bytes = r.ss_text_off[1] - r.ss_text_off[0];  /* r is valid until the next batch */
+    /* the same read named by coordinates against a genome resident on the GPU (forward: identical signal; reverse: its
+     * reverse complement comes back through SQG_WANT_BASES) */
+    const int64_t coff[2] = {0, (int64_t)strlen(read)};
+    rc = sqg_genome_load(ctx, 1, read, coff, NULL, NULL);
+    if (rc != SQG_OK) { printf("genome_load failed %d %s\n", rc, sqg_last_error(ctx)); return 10; }
+    sqg_coord_t co[2];
+    memset(co, 0, sizeof co);
+    co[0].contig = 0; co[0].pos = 0; co[0].len = (int32_t)strlen(read); co[0].strand = '+';
+    co[1] = co[0]; co[1].strand = '-';
+    sqg_result_t rc2;
+    rc = sqg_gen_batch_coords(ctx, 2, co, 0, 0, SQG_WANT_BASES, &rc2);
+    if (rc != SQG_OK || rc2.n_reads != 2 || !rc2.bases || !rc2.signal) { printf("gen_batch_coords failed %d\n", rc); return 11; }
+    if (rc2.len_raw_signal[0] != len || memcmp(rc2.signal + rc2.sig_off[0], raw, (size_t)len * sizeof(int16_t)) != 0) {
+        printf("coordinate read differs from gen_sig\n"); return 12;
+    }
+    if (memcmp(rc2.bases + rc2.bases_off[0], read, strlen(read)) != 0) { printf("forward bases differ\n"); return 13; }
+    {
+        const size_t n = strlen(read);
+        const char *rv = rc2.bases + rc2.bases_off[1];
+        for (size_t i = 0; i < n; i++) {
+            const char f = read[n - 1 - i], want = f == 'A' ? 'T' : f == 'C' ? 'G' : f == 'G' ? 'C' : 'A';
+            if (rv[i] != want) { printf("reverse complement differs at %d\n", (int)i); return 14; }
+        }
+    }
+    printf("ok %lld %lld %lld %lld\n", (long long)len, (long long)ss_n, (long long)svb_bytes, (long long)text_bytes);
     free(raw); free(ss); free(two); free(model);
     sqg_destroy(ctx);
     return 0;
