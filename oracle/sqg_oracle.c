@@ -409,24 +409,30 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                 raw[n++] = to_i16_d((double)s * p->digitisation / p->range - offset);
             }
         } else {
-            /* Philox mode: single precision.  A' is rounded once by the product, B' once by the FMA, then B' is put
-             * on the 2^-8 grid: Bq = (B' + 32768) - 32768 in float arithmetic (for every sane profile B' + 32768
-             * lies in [32768, 65536), where floats are spaced 2^-8 apart).  The sample is the single-precision FMA
-             * z*A' + Bq ROUNDED TOWARD ZERO, truncated toward zero like the reference's store (src/gensig.c:270) and
-             * wrapped to 16 bits.  The GPU gets the same integer for 0 <= value < 32768 from the mantissa of
-             * fma.rz(z, A', Bq + 32768) without a conversion, and falls back to this very expression otherwise. */
+            /* Philox mode: single precision.  A' = (stdv*amp_noise)*scale and M = mean*scale are rounded once per product
+             * (they depend on the k-mer only: the GPU tabulates them), c_r = 32768 - (float)offset once per read, and
+             * Bm = M + c_r once per k-mer - for every sane profile Bm lies in [32768, 65536), where floats are spaced 2^-8
+             * apart, so Bq = Bm - 32768 is B' on the 2^-8 grid.  The sample is the single-precision FMA z*A' + Bq ROUNDED
+             * TOWARD ZERO, truncated toward zero like the reference's store (src/gensig.c:270) and wrapped to 16 bits.  The
+             * GPU gets the same integer for 0 <= value < 32768 from the mantissa of fma.rz(z, A', Bm) without a conversion,
+             * and falls back to this very expression otherwise. */
             const float scale_f = (float)scale, off_f = (float)offset;
             const float A = o->sd_eff[r] * scale_f;
-            const float B = fmaf(mean, scale_f, -off_f);
-            volatile float Bm = B + 32768.0f;
+            volatile float M = mean * scale_f;
+            volatile float c_r = 32768.0f - off_f;
+            volatile float Bm = M + c_r;
             const float Bq = Bm - 32768.0f;
             for (int j = 0; j < sps[i]; j++, n++) {
-                /* Philox draws are addressed by the position in the EMITTED signal (after the RNA
-                 * reversal of src/gensig.c:348-354), eight 10-bit draws per block */
+                /* Philox draws are addressed by the position in the EMITTED signal (after the RNA reversal of
+                 * src/gensig.c:348-354), eight 10-bit draws per block.  The draw's table class is the block's low five
+                 * bits XOR five hash bits of (block >> 5, read): a bijection of the 32 blocks of a group, different from
+                 * group to group, so no sample position is tied to one class. */
                 uint32_t q = (uint32_t)(rna ? total - 1 - n : n);
-                uint32_t ctr[4] = {q >> 3, r_lo, r_hi, ST_AMP}, w[4];
+                uint32_t blk = q >> 3;
+                uint32_t ctr[4] = {blk, r_lo, r_hi, ST_AMP}, w[4];
                 philox(ctr, o->key, w);
-                float z = sqo_z32(o->zt, zindex(w, q & 7, q >> 3), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
+                uint32_t h = ((blk >> 5) * 0x9E3779B1u + r_lo * 0x85EBCA6Bu) >> 27;
+                float z = sqo_z32(o->zt, zindex(w, q & 7, (blk & 31u) ^ h), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
                 raw[n] = to_i16_f(fma_rz(z, A, Bq));
             }
         }

@@ -26,6 +26,7 @@
 #include <cuda/functional>
 
 #include "sqg_kernels.cuh"
+#include "sqg_signal.cuh"
 #include "sqg_legacy.cuh"
 #include "sqg_svb.cuh"
 #include "sqg_sstext.cuh"
@@ -107,7 +108,7 @@ struct Slot {
     DevBuf<ReadDesc> d_reads;
     DevBuf<TileDesc> d_tiles;
     DevBuf<uint32_t> d_tile_sum, d_siglen, d_n0;
-    DevBuf<uint4> d_dwells;  // TK uint16 per tile (K1 -> K4)
+    DevBuf<uint4> d_kpos;  // TK uint16 per tile: prefix of the dwells within the tile (K1 -> K4)
     DevBuf<int64_t> d_sigoff, d_meta;
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
@@ -151,7 +152,7 @@ struct Slot {
     int64_t arena_need = 0, total_samples = 0;
     bool const_written = false;
     void release() {
-        d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release(); d_dwells.release();
+        d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release(); d_kpos.release();
         d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
         d_offset.release(); d_median.release(); d_sig.release(); d_ss.release();
         d_rank.release(); d_rank_sorted.release(); d_idx.release(); d_idx_sorted.release(); d_dsorted.release();
@@ -199,6 +200,7 @@ struct sqg_ctx {
     int num_sms = 0;
     std::string err;
     DevBuf<float2> d_model;
+    DevBuf<float2> d_model_am;    // (A', M) by rank (model_am_kernel)
     DevBuf<float4> d_pair_model;  // by (k+1)-mer: the parameters of both of its k-mers (base-4 models)
     DevBuf<float4> d_quad_model;  // k <= 6: by (k+3)-mer, the parameters of its four k-mers (32-byte entries)
     DevBuf<unsigned char> d_z;  // Z32 ++ Z2
@@ -412,7 +414,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     const size_t nt = (size_t)std::max<int64_t>(ntile, 1), nr = (size_t)std::max<int64_t>(n_reads, 1);
     CU(s.d_tiles.ensure(nt, false, s.stream));
     CU(s.d_tile_sum.ensure(nt, false, s.stream));
-    if (ctx->rand_dwell && !ctx->legacy) CU(s.d_dwells.ensure(nt * (TK / 8), false, s.stream));
+    if (ctx->rand_dwell && !ctx->legacy) CU(s.d_kpos.ensure(nt * (TK / 8), false, s.stream));
     CU(s.d_siglen.ensure(nr, false, s.stream));
     CU(s.d_n0.ensure(nr, false, s.stream));
     CU(s.d_sigoff.ensure(nr, false, s.stream));
@@ -484,7 +486,7 @@ int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_
 GenParams slot_params(sqg_ctx *ctx, Slot &s) {
     GenParams p = ctx->base;
     p.bases = s.d_bases.p; p.segs = s.d_segs.p; p.reads = s.d_reads.p;
-    p.tiles = s.d_tiles.p; p.tile_sum = s.d_tile_sum.p; p.dwells = s.d_dwells.p;
+    p.tiles = s.d_tiles.p; p.tile_sum = s.d_tile_sum.p; p.kpos = s.d_kpos.p;
     p.read_siglen = s.d_siglen.p; p.read_n0 = s.d_n0.p; p.read_sigoff = s.d_sigoff.p;
     p.read_offset = s.d_offset.p; p.read_median = s.d_median.p; p.meta = s.d_meta.p;
     p.sig = s.d_sig.p; p.ss = s.d_ss.p;
@@ -834,20 +836,37 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
             ctx->rand_dwell = false;
         }
     }
+    b.par_cap = PAR_N;
+    b.tile_s_cap = 0xFFFFFFFFu;
+    if (cfg->meth) b.pow5k = b.kmask * 5u;
     if (ctx->rand_dwell) {
         // largest possible dwell: |z| <= Z_MAX, folded values included
         const double mx = std::floor((double)b.dwell_mean + (double)Z_MAX * (double)b.dwell_std + 0.5) + 2.0;
         if (!(mx < 1200.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 6.06*dwell_std too large for one tile");
-        int T = (int)((MAPC * 8 - 16) / (int)mx) & ~7;
-        b.T = std::max(8, std::min(T, TK));
+        // k-mers per tile: as many as keep a tile's samples inside the signal kernel's window even for a six-sigma run of
+        // long dwells (mean of the folded normal <= mean + std); a tile beyond TILE_S_CAP would still be generated
+        // correctly, by that kernel's slow path.  T * mx < 2^16: the dwell kernel stores 16-bit prefixes.
+        int T = TK;
+        const double dm = (double)b.dwell_mean + (double)b.dwell_std, ds = (double)b.dwell_std;
+        while (T > 8 && (T * dm + 6.0 * ds * std::sqrt((double)T) > (double)TILE_S_CAP || T * mx >= 65000.0)) T -= 8;
+        b.T = T;
+        b.tile_s_cap = TILE_S_CAP;
     } else {
-        // n / sps == umulhi(n, magic) needs n * sps < 2^32 for every tile sample n < T * sps
+        // n / sps == umulhi(n, magic) needs n * sps < 2^32 for every window sample n < par_cap * sps
         const uint64_t sps = (uint64_t)b.sps_fixed;
-        if (sps > 20000) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
-        uint64_t T = std::min<uint64_t>(TK, (0xFFFFFFFFull / (sps * sps)) & ~7ull);
-        if (T < 8) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
-        b.T = (int32_t)T;
+        if (sps > 16000) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
+        const uint64_t kcap = std::min<uint64_t>(PAR_N, 0xFFFFFFFFull / (sps * sps));   // k-mers in the window at most
+        if (kcap < 12) return fail(ctx, SQG_ERR_ARG, "dwell_mean too large");
+        b.par_cap = (int32_t)kcap;
+        b.T = (int32_t)std::min<uint64_t>(TK, (kcap - 4) & ~7ull);
         b.sps_magic = sps == 1 ? 0u : (uint32_t)(0x100000000ull / sps) + 1u;  // sps == 1 is special-cased in div_sps()
+    }
+    if (cfg->reserved > 0) {
+        // testing knob: shrink the window (low 16 bits: samples per tile the fast path accepts; high bits: k-mers) so that
+        // small inputs reach the cut-run and slow-tile paths
+        const uint32_t sc = (uint32_t)cfg->reserved & 0xFFFFu, kc = (uint32_t)cfg->reserved >> 16;
+        if (sc && ctx->rand_dwell) b.tile_s_cap = std::min<uint32_t>(b.tile_s_cap, sc);
+        if (kc) b.par_cap = std::max<int32_t>(b.T + 2, std::min<int32_t>(b.par_cap, (int32_t)kc));
     }
     for (int r = 0; r < PHILOX_ROUNDS; r++) {
         b.rk[2 * r] = b.key0 + (uint32_t)r * 0x9E3779B9u;
@@ -879,24 +898,32 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
         CU(cudaMemset(ctx->d_cnt_kmer.p, 0, n * sizeof(uint64_t)));
     }
     ctx->base.model = ctx->d_model.p;
-    if (!ctx->meth && !ctx->legacy) {
-        // the model again, indexed by (k+1)-mer: one 16-byte gather serves two consecutive k-mers (pair_model_kernel)
+    if (!ctx->legacy) {
+        // the model in the form the sample arithmetic uses: (A', M) by rank (model_am_kernel)
+        CU(ctx->d_model_am.ensure(n));
+        model_am_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->d_model.p, ctx->d_model_am.p, (uint32_t)n, ctx->cfg.amp_noise, (float)ctx->base.scale);
+        CU(cudaGetLastError());
+        ctx->base.model_am = ctx->d_model_am.p;
+    }
+    if (!ctx->meth && !ctx->legacy && ctx->noisy) {
+        // the same, indexed by (k+1)-mer: one 16-byte gather serves two consecutive k-mers (pair_model_kernel)
         const uint64_t n_pair = 4ull * n;
         if (n_pair * sizeof(float4) > (256ull << 20)) return fail(ctx, SQG_ERR_ARG, "k-mer size too large for the paired model table");
         CU(ctx->d_pair_model.ensure((size_t)n_pair));
-        pair_model_kernel<<<(unsigned)((n_pair + 255) / 256), 256>>>(ctx->d_model.p, ctx->d_pair_model.p, (uint32_t)n_pair, ctx->base.kmask);
+        pair_model_kernel<<<(unsigned)((n_pair + 255) / 256), 256>>>(ctx->d_model_am.p, ctx->d_pair_model.p, (uint32_t)n_pair, ctx->base.kmask);
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
         ctx->base.pair_model = ctx->d_pair_model.p;
         if (ctx->cfg.kmer_size <= 6 && ctx->cfg.kmer_size >= 1) {
             const uint64_t n_quad = 64ull * n;   // 4^(k+3)
             CU(ctx->d_quad_model.ensure((size_t)(2 * n_quad)));
-            quad_model_kernel<<<(unsigned)((n_quad + 255) / 256), 256>>>(ctx->d_model.p, ctx->d_quad_model.p, (uint32_t)n_quad, ctx->base.kmask);
+            quad_model_kernel<<<(unsigned)((n_quad + 255) / 256), 256>>>(ctx->d_model_am.p, ctx->d_quad_model.p, (uint32_t)n_quad, ctx->base.kmask);
             CU(cudaGetLastError());
             CU(cudaDeviceSynchronize());
             ctx->base.quad_model = ctx->d_quad_model.p;
         }
     }
+    CU(cudaDeviceSynchronize());
     ctx->base.z32 = reinterpret_cast<const float *>(ctx->d_z.p);
     ctx->base.z2 = reinterpret_cast<const float *>(ctx->d_z.p + (size_t)Z32_BYTES);
 
@@ -1008,6 +1035,9 @@ void sqg_destroy(sqg_ctx_t *ctx) {
     for (auto &s : ctx->slots) s.release();
     ctx->sync_slot.release();
     ctx->d_model.release();
+    ctx->d_model_am.release();
+    ctx->d_pair_model.release();
+    ctx->d_quad_model.release();
     ctx->d_z.release();
     ctx->d_cnt_kmer.release();
     ctx->d_genome.release(); ctx->d_gmeth.release(); ctx->d_has_meth.release(); ctx->d_contig_off.release();

@@ -1,0 +1,837 @@
+// sqg_signal.cuh — K4, the signal kernel (sm_100a, hand-written): src/gensig.c:226-288 for a whole batch.
+//
+// Work decomposition.  The batch's TILES (<= 256 consecutive k-mers of one read segment, sqg_kernels.cuh) form one
+// global sequence; every WARP takes a contiguous range of it and walks it autonomously (no CTA barrier after the
+// prologue).  Within a read the warp keeps a SLIDING WINDOW in shared memory:
+//   par[]  (A', B) of the registered k-mers                       (B = M + c_r: one FADD per k-mer, see model_am_kernel)
+//   map[]  per 32 samples {bit s: a k-mer starts at sample s, index of the k-mer that owns the entry's first sample}
+// phase A registers the next tile's k-mers (digits -> ranks -> table gathers; start bits from the tile-relative prefix the
+// dwell kernel stored), phase B emits every GROUP of 256 samples (32 lanes x one 16-byte chunk) that has become complete,
+// then the k-mers still needed (those of the incomplete group) are moved to the front of the window.  Groups are aligned
+// in the EMITTED signal, so:
+//   * every store of the bulk is a full, aligned 16-byte chunk - nothing is clipped at tile boundaries;
+//   * lane = emitted chunk & 31, so a warp-wide table lookup touches 32 different banks whatever bijection of the lanes
+//     the group's class rotation applies;
+//   * only where a warp's range begins or ends inside a read is a chunk shared with another warp: those (<= 2 per range)
+//     take the exact path, which stores sample by sample.
+// Everything a tile needs from global memory (descriptor, base window, prefix row, its read's offset/length/arena
+// position) is fetched one tile ahead with cp.async (LDGSTS) while the previous tile's samples are being emitted.
+//
+// Shared memory (byte offsets into the dynamic array, all compile-time so that they fold into LDS/STS immediates):
+//   [Z32: 128 KB quantile table (TMA bulk copy)] [code: 256 B] [mbar] [per warp: map, par, raw window, digits, prefix, descriptors]
+#pragma once
+#include <type_traits>
+
+#include "sqg_kernels.cuh"
+
+namespace sqg {
+
+#ifndef SQG_K4_WARPS
+#define SQG_K4_WARPS 16
+#endif
+constexpr int K4_WARPS = SQG_K4_WARPS;
+constexpr int K4_THREADS = K4_WARPS * 32;  // register budget: 65536 / 512 = 128
+constexpr uint32_t GROUP_S = 256;          // samples per group: 32 lanes x 8
+constexpr int PAR_TAIL = 128;              // k-mers carried from tile to tile at most (else the run is cut)
+constexpr int PAR_N = TK + PAR_TAIL;       // registered k-mers at most
+constexpr int MAP_ENT = 168;               // map entries (32 samples each): window of 5376 samples
+constexpr uint32_t TILE_S_CAP = MAP_ENT * 32 - GROUP_S - 64;   // samples of one tile the window is guaranteed to hold
+constexpr int DIG_BYTES = TK + 32;         // digits of the tile's base window; the same size holds the raw window (16-byte granules)
+// per-warp buffer
+constexpr uint32_t W_MAP = 0;                               // MAP_ENT (+2 that the one-ahead loads may touch) x {bits, base}
+constexpr uint32_t W_PARG = W_MAP + (MAP_ENT + 2) * 8;      // guard entry par[-1] (the padding chunk of a reversed read)
+constexpr uint32_t W_PAR = W_PARG + 16;                     // par[0 .. PAR_N) + 4 rows the sample loop may load past the end
+constexpr uint32_t W_RAW = W_PAR + (PAR_N + 4) * 8;         // prefetched base window (ASCII), 16-byte granules
+constexpr uint32_t W_DIG = W_RAW + DIG_BYTES;               // base digits (table path only)
+constexpr uint32_t W_PL = W_DIG + DIG_BYTES;                // prefetched prefix row of the tile: TK x uint16
+constexpr uint32_t W_DESC = W_PL + TK * 2;                  // two TileDesc slots
+constexpr uint32_t W_RD = W_DESC + 2 * 48;                  // two slots of {arena offset (8), samples in the read (4), pad, ADC offset (8), pad}
+constexpr uint32_t WARP_BYTES = W_RD + 2 * 32;
+constexpr uint32_t SM_Z = 0;
+constexpr uint32_t SM_CODE = SM_Z + Z32_BYTES;
+constexpr uint32_t SM_MBAR = SM_CODE + 256;
+constexpr uint32_t SM_WARP = SM_MBAR + 16;
+constexpr uint32_t SM_TOTAL = SM_WARP + K4_WARPS * WARP_BYTES;
+static_assert(SM_WARP % 16 == 0 && WARP_BYTES % 16 == 0 && W_PAR % 16 == 0 && W_RAW % 16 == 0 && W_DIG % 16 == 0 && W_PL % 16 == 0 &&
+              W_DESC % 16 == 0 && W_RD % 16 == 0, "alignment");
+static_assert(SM_TOTAL <= 232448, "227 KB of shared memory per CTA");
+static_assert(PAR_N % 2 == 0 && TK == 256, "layout assumptions");
+
+// ---- per-lane asynchronous global -> shared copies (SASS: LDGSTS) for the next tile's inputs ----
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+// shared-window address of a pointer, computed behind an opaque asm: the compiler must not tie the (vector-register)
+// addresses of the asynchronous copies to the base of the ordinary shared-memory accesses, which it keeps in a uniform
+// register ([R + UR + imm] addressing in the sample loop)
+__device__ __forceinline__ uint32_t opaque_smem_addr(const void *sptr) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(sptr));
+    return a;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#ifndef SQG_ST_POLICY
+#define SQG_ST_POLICY ".cs"   // streaming (evict-first) stores: the signal is written once and never read back by the kernel
+#endif
+__device__ __forceinline__ void st_cs_v4(void *gptr, uint4 v) {
+    asm volatile("st.global" SQG_ST_POLICY ".v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- shared-memory loads of the sample loop, by absolute shared-window address with the constant part as an
+// immediate.  The dynamic array starts right after the driver's reserved kilobyte (cudaDevAttrReservedSharedMemoryPerBlock;
+// this kernel has no static shared memory), so `offset + SMEM_ORIGIN + constant` needs no base register: one LOP3 makes
+// the table offset and the load takes it as is.  The kernel prologue checks the origin and refuses to run otherwise. ----
+constexpr uint32_t SMEM_ORIGIN = 0x400;
+template <uint32_t IMM>
+__device__ __forceinline__ float lds_f32(uint32_t off) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+    return v;
+}
+template <uint32_t IMM>
+__device__ __forceinline__ float2 lds_f2(uint32_t off) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+    return v;
+}
+template <uint32_t IMM>
+__device__ __forceinline__ uint2 lds_u2(uint32_t off) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(off), "n"(SMEM_ORIGIN + IMM) : "memory");
+    return v;
+}
+
+// ---- the amplitude draws.  The sample at position q of the EMITTED signal uses draw q & 7 of Philox
+// block q >> 3 (stream ST_AMP); its table CLASS is (block & 31) ^ h, h = five hash bits of the block's group of 32
+// (and of the read): within a group the classes are a bijection of the lanes - one bank per lane - and over the groups
+// every position of the signal meets every class.
+__device__ __forceinline__ uint32_t amp_class_hash(uint32_t group, uint32_t hmul) { return (group * 0x9E3779B1u + hmul) >> 27; }
+__device__ __forceinline__ uint32_t amp_class4(uint32_t Cq, uint32_t hmul) { return ((Cq & 31u) ^ amp_class_hash(Cq >> 5, hmul)) << 2; }
+__device__ __forceinline__ uint32_t amp_hmul(uint32_t r_lo) { return r_lo * 0x85EBCA6Bu; }
+
+// What a warp knows about the run it is in: consecutive tiles of one read, from where the warp's range (or the read)
+// begins to where it ends.  FRAME coordinates f count samples in generation order from a point <= the run's first
+// sample chosen such that f = 0 (mod 256) is a group boundary of the emitted signal.  All warp-uniform.
+struct Run {
+    uint32_t C0;          // emitted chunk (= Philox block) of frame chunk 0: frame chunk c is C0 + c, or C0 - c when reversed
+    uint32_t r_lo, r_hi;  // global read index (Philox counter words 1, 2)
+    uint32_t hmul;        // amp_hmul(r_lo)
+    int16_t *out;         // start of the read in the signal arena
+    float c_r;            // 32768 - (float)offset  (noisy modes)
+    double offset;        // the read's ADC offset
+    uint32_t L;           // samples in the read
+    uint32_t clip_lo;     // first frame sample this run owns (0: the run starts its read - what lies before is padding)
+    uint32_t f_end;       // one past the last registered frame sample
+    uint32_t fmap;        // frame coordinate of map entry 0 (a multiple of 256)
+    uint32_t cur_c;       // next frame chunk to emit
+    int32_t nreg;         // k-mers in par[]
+    int32_t last_e;       // map entry holding the first sample of the last registered k-mer (-1: none, or before the map)
+    int32_t fix_f0;       // fixed-dwell modes: frame coordinate of the first sample of par[0]'s k-mer
+};
+
+// per-lane constants of the sample loop
+struct LaneC {
+    uint32_t lw;        // the lane's chunk within a group in FRAME order (reversed reads: 31 - lane)
+    uint32_t ent_sh;    // 8 * (lw & 3): the chunk's byte within its map entry
+    uint32_t ent_lane;  // 8 * (lw >> 2): byte offset of its entry within the group's eight
+    uint32_t lane4;     // lane << 2
+};
+
+// k-mer (index into par[]) of a chunk's first sample and the chunk's boundary mask (bit j, 1..7: a k-mer starts at slot j
+// in generation order).  A start on the chunk's first sample is not a boundary to cross.
+__device__ __forceinline__ void entry_kmers(uint2 ent, uint32_t sh, uint32_t &k0, uint32_t &m1) {
+    k0 = ent.y + __popc(ent.x & ((2u << sh) - 1u));
+    m1 = (ent.x >> sh) & 0xFEu;
+}
+template <bool RAND_DWELL>
+__device__ __forceinline__ void chunk_kmers(const GenParams &p, const unsigned char *smem, uint32_t map_off, uint32_t fmap, int32_t fix_f0,
+                                            uint32_t c, uint32_t &k0, uint32_t &m1) {
+    if (RAND_DWELL) {
+        entry_kmers(*reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * ((8 * c - fmap) >> 5)), 8 * (c & 3), k0, m1);
+    } else {
+        const int s0 = (int)(8 * c) - fix_f0;
+        k0 = div_sps(p, (uint32_t)max(s0, 0));
+        m1 = 0;
+        for (int b = (int)((k0 + 1) * (uint32_t)p.sps_fixed) - s0; b < 8; b += p.sps_fixed) m1 |= 1u << b;
+    }
+}
+
+// ---- phase B ---------------------------------------------------------------------------------------------------
+
+// The exact path of one chunk, start to finish (rare: a chunk shared with another warp's range, a chunk with a flagged
+// sample - tail cell of the table, negative value, value beyond int16 - or with four or more k-mers, and every chunk in
+// wide mode): samples are trunc(fma.rz(z, A', Bq)) with the tail cells refined and any number of boundaries; only frame
+// samples in [clip_lo, clip_hi) are stored.  par[] holds B'+32768 (or Bq itself in wide mode).
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char *smem, uint32_t map_off, uint32_t fmap, int32_t fix_f0,
+                                         uint32_t C0, uint32_t r_lo, uint32_t r_hi, uint32_t hmul, int16_t *out, uint32_t c,
+                                         uint32_t clip_lo, uint32_t clip_hi) {
+    uint32_t k0, m1;
+    chunk_kmers<RAND_DWELL>(p, smem, map_off, fmap, fix_f0, c, k0, m1);
+    const uint32_t par0 = k0 * 8 + map_off + W_PAR;
+    const uint32_t Cq = REV ? C0 - c : C0 + c;
+    const uint32_t class4 = amp_class4(Cq, hmul);
+    const RngKey key{p.key0, p.key1, r_lo, r_hi};
+    uint4 r4 = make_uint4(0, 0, 0, 0);
+    if (NOISY) r4 = philox4x32_rk(Cq, r_lo, r_hi, ST_AMP, p.rk);
+    const float sub = p.wide ? 0.f : SAMPLE_MAGIC;
+    int16_t *dst = out + (size_t)Cq * 8;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int j = REV ? 7 - e : e;
+        const uint32_t f = 8 * c + j;
+        if (f >= clip_lo && f < clip_hi) {
+            const float2 ab = *reinterpret_cast<const float2 *>(smem + par0 + 8 * __popc(m1 & ((2u << j) - 1u)));
+            uint32_t v;
+            if (NOISY) {
+                const uint32_t off = z_offset(draw_word(r4, e), class4);
+                float z = *reinterpret_cast<const float *>(smem + SM_Z + off);
+                if (z_is_tail(off)) z = z_tail(p.z2, off, Cq * 8 + e, key, ST_AMP_TAIL);
+                v = sample_exact(z, ab.x, __fsub_rn(ab.y, sub));
+            } else {
+                v = __float_as_uint(ab.y);
+            }
+            dst[e] = (int16_t)v;
+        }
+    }
+}
+
+// One chunk = 8 consecutive samples = at most 3 k-mers on the fast path: the parameters of k-mers k0, k0+1, k0+2 are
+// loaded once (three 8-byte loads) and every sample picks its own by PREDICATE - the k-mer boundaries inside the
+// chunk arrive as a bit mask, `mask-1` has its bits clear exactly from the first boundary upwards, and one R2P moves
+// seven of those bits into predicate registers - so a sample costs one FFMA plus at most two predicated ones on the
+// FMA pipe, and no shared-memory traffic of its own.  Returns non-zero when the chunk has to be redone by the exact path
+// (flagged sample, 4+ k-mers).
+template <bool NOISY, bool REV>
+__device__ __forceinline__ uint32_t fast_chunk(const GenParams &p, uint32_t k0, uint32_t m1, uint32_t par_base, uint32_t Cq,
+                                               uint32_t class4, uint32_t r_lo, uint32_t r_hi, int16_t *out) {
+    const uint32_t par0 = k0 * 8 + par_base;
+    const float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0), q2 = lds_f2<16>(par0);
+    const uint32_t t1 = m1 - 1u;        // bit j clear  <=>  slot j lies at or after the 1st boundary
+    const uint32_t m2 = m1 & t1;        // boundaries after the first
+    const uint32_t t2 = m2 - 1u;        // bit j clear  <=>  slot j lies at or after the 2nd boundary
+    const uint32_t m3 = m2 & t2;        // non-zero: a 3rd boundary -> exact path
+    uint4 pk;
+    uint32_t bad;
+    if (NOISY) {
+        const uint4 r4 = philox4x32_rk(Cq, r_lo, r_hi, ST_AMP, p.rk);
+        float zz[8], v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {   // e = slot in the emitted chunk = which draw; j = slot in generation order
+            zz[e] = lds_f32<SM_Z>(z_offset(draw_word(r4, e), class4));
+            v[e] = fma_rz(zz[e], q0.x, q0.y);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {   // level by level, so that one R2P per level sets the predicates
+            const int j = REV ? 7 - e : e;
+            if (j >= 1 && !(t1 & (1u << j))) v[e] = fma_rz(zz[e], q1.x, q1.y);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = REV ? 7 - e : e;
+            if (j >= 2 && !(t2 & (1u << j))) v[e] = fma_rz(zz[e], q2.x, q2.y);
+        }
+        uint32_t u[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) u[e] = __float_as_uint(v[e]);
+        // bits 8..23 of each float, packed little-endian
+        pk = make_uint4(__byte_perm(u[0], u[1], 0x6521), __byte_perm(u[2], u[3], 0x6521),
+                        __byte_perm(u[4], u[5], 0x6521), __byte_perm(u[6], u[7], 0x6521));
+        bad = ((pk.x | pk.y | pk.z | pk.w) & 0x80008000u) | m3;
+    } else {
+        uint32_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = REV ? 7 - e : e;
+            float x = q0.y;
+            if (j >= 1 && !(t1 & (1u << j))) x = q1.y;
+            if (j >= 2 && !(t2 & (1u << j))) x = q2.y;
+            v[e] = __float_as_uint(x);
+        }
+        // low 16 bits of each int32 (the reference's wrap, src/gensig.c:270), packed little-endian
+        pk = make_uint4(__byte_perm(v[0], v[1], 0x5410), __byte_perm(v[2], v[3], 0x5410),
+                        __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
+        bad = m3;
+    }
+    st_cs_v4(out + (size_t)Cq * 8, pk);
+    return bad;
+}
+
+// One group of 32 chunks.  FAST: all of them are whole and owned.  Otherwise only frame chunks [c_lo, c_hi) are emitted,
+// and those reaching outside [clip_lo, clip_hi) - or all of them when `all_exact` - take the exact path.
+template <bool NOISY, bool RAND_DWELL, bool REV, bool FAST>
+__device__ __forceinline__ void emit_group(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
+                                           uint32_t g, uint32_t c_lo, uint32_t c_hi, uint32_t clip_hi, bool all_exact) {
+    const uint32_t c = 32 * g + lc.lw;
+    const uint32_t Cq = REV ? t.C0 - c : t.C0 + c;
+    if (!FAST) {
+        if (c < c_lo || c >= c_hi) return;
+        if (all_exact || 8 * c < t.clip_lo || 8 * c + 8 > clip_hi) {
+            exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, map_off, t.fmap, t.fix_f0, t.C0, t.r_lo, t.r_hi, t.hmul, t.out, c, t.clip_lo, clip_hi);
+            return;
+        }
+    }
+    uint32_t k0, m1;
+    if (RAND_DWELL) {
+        const uint2 ent = lds_u2<W_MAP>(map_off + 64 * (g - (t.fmap >> 8)) + lc.ent_lane);
+        entry_kmers(ent, lc.ent_sh, k0, m1);
+    } else {
+        chunk_kmers<false>(p, smem, map_off, t.fmap, t.fix_f0, c, k0, m1);
+    }
+    // (Cq >> 5 is the same for all lanes of a group: groups are aligned in the emitted signal)
+    const uint32_t class4 = lc.lane4 ^ (amp_class_hash(Cq >> 5, t.hmul) << 2);
+    const uint32_t bad = fast_chunk<NOISY, REV>(p, k0, m1, map_off + W_PAR, Cq, class4, t.r_lo, t.r_hi, t.out);
+    if (__builtin_expect(bad != 0, 0))
+        exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, map_off, t.fmap, t.fix_f0, t.C0, t.r_lo, t.r_hi, t.hmul, t.out, c, 0u, 0xFFFFFFFFu);
+}
+
+// Emit what has become complete.  `last`: the run ends with the samples registered so far.
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned char *smem, Run &t, const LaneC &lc, uint32_t map_off, bool last,
+                                           uint32_t clip_hi) {
+    const uint32_t hi_c = last ? (t.f_end + 7) >> 3 : t.f_end >> 3;   // chunks below hi_c can be computed
+    const bool all_exact = NOISY && p.wide;
+    while (t.cur_c < hi_c) {
+        const uint32_t g = t.cur_c >> 5;
+        if (!all_exact && (t.cur_c & 31u) == 0 && 8 * t.cur_c >= t.clip_lo) {
+            // whole groups: [g, g_end)
+            const uint32_t lim = min(hi_c, clip_hi >> 3);
+            const uint32_t g_end = lim >> 5;
+            if (g < g_end) {
+#pragma unroll 2
+                for (uint32_t gg = g; gg < g_end; gg++) emit_group<NOISY, RAND_DWELL, REV, true>(p, smem, t, lc, map_off, gg, 0, 0, 0, false);
+                t.cur_c = 32 * g_end;
+                continue;
+            }
+        }
+        const uint32_t gend_c = 32 * (g + 1);
+        if (!last && gend_c > hi_c) break;   // the group completes with the next tile
+        const uint32_t ce = min(gend_c, hi_c);
+        emit_group<NOISY, RAND_DWELL, REV, false>(p, smem, t, lc, map_off, g, t.cur_c, ce, clip_hi, all_exact);
+        t.cur_c = ce;
+    }
+}
+
+// ---- phase A ---------------------------------------------------------------------------------------------------
+
+constexpr int WIN_LOADS = (TK + 8 + 31) / 32;  // bytes per lane of a tile's base window (k <= 9)
+
+// a tile whose base window straddles the two pieces of its segment (only around a --prefix junction)
+__device__ __forceinline__ bool tile_is_junction(const GenParams &p, int32_t a_rem, int32_t nk) {
+    return a_rem > 0 && a_rem < nk + p.k - 1;
+}
+
+// Asynchronous fetch of a tile's inputs into the warp's buffer: the base window as 16-byte granules (the aligned
+// superset of the window), its prefix row, its read's arena offset / length / ADC offset.  `desc_off` = the tile's
+// descriptor, already in shared memory.
+template <bool RAND_DWELL>
+__device__ __forceinline__ void fetch_tile_inputs(const GenParams &p, const unsigned char *smem, uint32_t wbase, uint32_t desc_off,
+                                                  uint32_t rd_rel, int tile, int lane) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(smem + desc_off);
+    const uint4 b = *reinterpret_cast<const uint4 *>(smem + desc_off + 16);
+    const int32_t a_rem = (int32_t)b.x, nk = (int32_t)(b.y & 0xFFFFu), read = (int32_t)b.z;
+    if (!tile_is_junction(p, a_rem, nk)) {
+        const int64_t off = a_rem > 0 ? (int64_t)(((uint64_t)a.y << 32) | a.x) : (int64_t)(((uint64_t)a.w << 32) | a.z);
+        const uint8_t *g = p.bases + off;
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+        const uint32_t nbytes = shift + (uint32_t)(nk + p.k - 1);
+        if ((uint32_t)lane * 16 < nbytes) cp_async16(wbase + W_RAW + lane * 16, g - shift + lane * 16);
+    }
+    if (RAND_DWELL) cp_async16(wbase + W_PL + lane * 16, p.kpos + (size_t)tile * (TK / 8) + lane);
+    if (lane == 0) cp_async8(wbase + rd_rel, p.read_sigoff + read);
+    if (lane == 1) cp_async4(wbase + rd_rel + 8, p.read_siglen + read);
+    if (lane == 2) cp_async8(wbase + rd_rel + 16, p.read_offset + read);
+}
+__device__ __forceinline__ void fetch_tile_desc(const GenParams &p, uint32_t wbase, uint32_t desc_rel, int tile, int lane) {
+    if (lane < 3) cp_async16(wbase + desc_rel + lane * 16, reinterpret_cast<const uint4 *>(p.tiles + tile) + lane);
+}
+
+struct TileIn {   // the descriptor fields phase A works from (warp-uniform)
+    int64_t a_off, b_off;
+    int32_t a_rem, nk;
+    uint32_t S;
+};
+
+// Phase A of one tile: its k-mers are appended to the run's window.  Descriptor, base window and prefix row are already
+// in the warp's buffer.
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
+__device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsigned char *smem, uint32_t map_off, Run &t, const TileIn &td) {
+    constexpr bool SINGLE = METH || !NOISY;   // one gather per k-mer from a table indexed by rank
+    const int nk_tile = td.nk;
+    const int nb = nk_tile + p.k - 1;
+    const uint32_t dig_off = map_off + W_DIG;
+    const int m0 = lane * 8;
+
+    // (1) bases -> digits.  Fast path (base-4 models, window in one piece): every lane takes the 16 raw bytes of its own
+    // 8 k-mers straight from the prefetched window (three aligned 8-byte loads + a funnel shift by the window's
+    // misalignment) and turns A/C/G/T of either case into digits arithmetically, ((c>>1) ^ (c>>2)) & 3, four bytes at
+    // a time; a PRMT maps the digits back to letters to check that every byte really was one of those eight.  Any
+    // other byte in the tile (IUPAC codes, U, N: src/seq.h:14-28 folds them) sends the whole warp through the
+    // 256-entry code table, which is also the path of base-5 (CpG) models (src/seq.h:45-60) and of prefix junctions.
+    uint32_t dg[4] = {0, 0, 0, 0};   // the lane's 16 digits, one per byte
+    bool table_path = METH || tile_is_junction(p, td.a_rem, nk_tile);
+    if (!table_path) {
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
+        const uint32_t s0 = shift + 8u * (uint32_t)lane;     // lane's first byte within the raw buffer
+        const uint2 *rw = reinterpret_cast<const uint2 *>(smem + map_off + W_RAW + (s0 & ~7u));
+        const uint2 w0 = rw[0], w1 = rw[1], w2 = rw[2];
+        const bool hi = (s0 & 4u) != 0;                       // (warp-uniform: shift & 4)
+        const uint32_t q0 = hi ? w0.y : w0.x, q1 = hi ? w1.x : w0.y, q2 = hi ? w1.y : w1.x, q3 = hi ? w2.x : w1.y, q4 = hi ? w2.y : w2.x;
+        const uint32_t fs = 8u * (s0 & 3u);
+        const uint32_t x[4] = {__funnelshift_r(q0, q1, fs), __funnelshift_r(q1, q2, fs), __funnelshift_r(q2, q3, fs), __funnelshift_r(q3, q4, fs)};
+        uint32_t bad = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t c = ((x[i] >> 1) ^ (x[i] >> 2)) & 0x03030303u;
+            const uint32_t u = (c | (c >> 4)) & 0x00FF00FFu;
+            const uint32_t sel = (u | (u >> 8)) & 0xFFFFu;                    // the four digits as PRMT selectors
+            bad |= __byte_perm(0x54474341u /* "ACGT" */, 0u, sel) ^ (x[i] & 0xDFDFDFDFu);
+            dg[i] = c;
+        }
+        // bytes past the window's end are whatever the 16-byte granules held: harmless as digits, but they must not
+        // force the table path, so only the lane's bytes inside the window count
+        const int inside = nb - 8 * lane;
+        if (inside < 16) {
+            if (inside <= 0) bad = 0;
+            else {
+                uint32_t keep = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int nbytes = min(max(inside - 4 * i, 0), 4);
+                    const uint32_t m = nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+                    const uint32_t c = dg[i];
+                    const uint32_t u = (c | (c >> 4)) & 0x00FF00FFu;
+                    const uint32_t sel = (u | (u >> 8)) & 0xFFFFu;
+                    keep |= (__byte_perm(0x54474341u, 0u, sel) ^ (x[i] & 0xDFDFDFDFu)) & m;
+                }
+                bad = keep;
+            }
+        }
+        table_path = __any_sync(0xffffffffu, bad != 0);
+    }
+    if (table_path) {
+        if (!tile_is_junction(p, td.a_rem, nk_tile)) {
+            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
+            const uint32_t raw_off = map_off + W_RAW + shift + lane;
+#pragma unroll 1
+            for (int u = 0; u < WIN_LOADS; u++) {
+                const int i = lane + 32 * u;
+                if (i < nb) {
+                    const uint32_t c = smem[SM_CODE + smem[raw_off + 32 * u]];
+                    smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = lane; i < nb; i += 32) {
+                const uint32_t c = smem[SM_CODE + __ldg(p.bases + (i < td.a_rem ? td.a_off : td.b_off) + i)];
+                smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
+            }
+        }
+        __syncwarp();
+        // (digits past the window are stale bytes of an earlier tile: they only reach k-mers past the tile's end)
+        const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
+        const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
+        dg[0] = dwa.x; dg[1] = dwa.y; dg[2] = dwb.x; dg[3] = dwb.y;
+        __syncwarp();   // (the digit buffer is rewritten by this warp's next tile)
+    }
+
+    // (1b) the table gathers of this lane are issued now, so that their L2 latency runs under the shared-memory work of
+    // step (2).  Base-4 models: 16 two-bit digits packed first-digit-most-significant
+    // (((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes); k-mers 2j, 2j+1 of the lane = the two k-mers of the
+    // (k+1)-mer at digit 2j: ONE 16-byte gather for both.  The four pairs are visited in ROTATED order
+    // jj(j) = (j + lane/2) & 3 so that the 16-byte parameter stores of a quarter-warp fall into 8 different bank groups.
+    float4 mv4[4];
+    float2 mv[8];
+    const int rot4 = lane >> 1;
+    if (!METH) {
+        const uint32_t P = ((((dg[0] & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dg[1] & 0x03030303u) * 0x40100401u) >> 24) << 16) |
+                           ((((dg[2] & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dg[3] & 0x03030303u) * 0x40100401u) >> 24);
+        if (SINGLE) {
+            const float2 *tab = p.model;   // (ideal amplitudes: the raw level_mean, in double below)
+            const int sh0 = 32 - 2 * p.k;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t r = (P >> (sh0 - 2 * j)) & p.kmask;
+                if (nk_tile < TK && m0 + j >= nk_tile) r = 0;
+                mv[j] = __ldg(&tab[r]);
+            }
+        } else if (QUAD) {
+            // k <= 6: two 256-bit gathers, each the four k-mers of one (k+3)-mer = one whole sector
+            const int shq = 26 - 2 * p.k;             // 32 - 2(k+3)
+            const uint32_t qmask = (p.kmask << 6) | 63u;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t r = (P >> (shq - 8 * h)) & qmask;
+                if (nk_tile < TK && m0 + 4 * h >= nk_tile) r = 0;
+                const float4 *src = p.quad_model + 2 * (size_t)r;
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(mv4[2 * h].x), "=f"(mv4[2 * h].y), "=f"(mv4[2 * h].z), "=f"(mv4[2 * h].w), "=f"(mv4[2 * h + 1].x),
+                               "=f"(mv4[2 * h + 1].y), "=f"(mv4[2 * h + 1].z), "=f"(mv4[2 * h + 1].w)
+                             : "l"(src));
+            }
+        } else {
+            const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
+            const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t r = (P >> (sh0 - 4 * ((j + rot4) & 3))) & pmask;
+                if (nk_tile < TK && m0 + 2 * ((j + rot4) & 3) >= nk_tile) r = 0;
+                mv4[j] = __ldg(&p.pair_model[r]);
+            }
+        }
+    } else {
+        // base-5 (CpG) ranks, src/seq.h:62-74, rolled: rank' = 5*rank - 5^k*(leading digit) + (new digit)
+        const float2 *tab = NOISY ? p.model_am : p.model;
+        const uint32_t dw[4] = {dg[0], dg[1], dg[2], dg[3]};
+        const int km1 = p.k - 1;
+        uint32_t rank = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < km1) rank = rank * 5 + ((dw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int bi = km1 + j;
+            const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
+            rank = rank * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);             // k digits: the k-mer at lane position j
+            mv[j] = __ldg(&tab[(m0 + j < nk_tile) ? rank : 0u]);
+            rank -= ((dw[j >> 2] >> (8 * (j & 3))) & 0xFFu) * p.kmask;        // drop its leading digit (kmask = 5^(k-1))
+        }
+    }
+
+    // (2) k-mer starts into the map.  Frame position of k-mer i of the tile = (frame position of the tile) + (prefix of
+    // the dwells before it, from K1): bit (pos & 31) of entry pos >> 5.  An entry's `base` is the par[] index of the k-mer
+    // that owns its first sample MINUS the number of starts... precisely: k-mer index = base + popcount(start bits at or
+    // before the sample); the first k-mer starting in an entry writes base = (its index - 1) there and into the empty
+    // entries between its predecessor's start and its own.
+    if (RAND_DWELL) {
+        const uint4 pq = *reinterpret_cast<const uint4 *>(smem + map_off + W_PL + lane * 16);
+        const uint32_t mrel = t.f_end - t.fmap;      // the tile's first sample, relative to map entry 0
+        const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+        uint32_t e[8], pos[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            pos[j] = mrel + ((j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xFFFFu));
+            e[j] = pos[j] >> 5;
+        }
+        int32_t ep = (int32_t)__shfl_up_sync(0xffffffffu, e[7], 1);
+        if (lane == 0) ep = t.last_e;
+        const int32_t idx0 = t.nreg + m0;
+        int32_t my_last = -1;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (nk_tile == TK || m0 + j < nk_tile) {
+                const uint32_t ea = map_off + W_MAP + 8 * e[j];
+                atomicOr(reinterpret_cast<uint32_t *>(smem + ea), __funnelshift_l(0u, 1u, pos[j]));
+                if ((int32_t)e[j] != ep) {
+                    for (int32_t x = ep + 1; x <= (int32_t)e[j]; x++) *reinterpret_cast<int32_t *>(smem + map_off + W_MAP + 8 * x + 4) = idx0 + j - 1;
+                }
+                ep = (int32_t)e[j];
+                my_last = ep;
+            }
+        }
+        // the last k-mer's start entry (entries are monotone over the lanes), and the entries it owns after that
+        const int32_t e_last = __reduce_max_sync(0xffffffffu, my_last);
+        const int32_t e_end = (int32_t)((mrel + td.S - 1) >> 5);
+        for (int32_t x = e_last + 1 + lane; x <= e_end; x += 32) *reinterpret_cast<int32_t *>(smem + map_off + W_MAP + 8 * x + 4) = t.nreg + nk_tile - 1;
+        t.last_e = e_last;
+    }
+
+    // (3) the parameters of this lane's 8 k-mers
+    const float c_r = t.c_r;
+    const double off_d = t.offset;
+    const bool wide = p.wide != 0;
+    auto make_par = [&](float a, float m) -> float2 {
+        if (NOISY) {
+            // (a, m) = (A', M): B' + 32768 = M + c_r, one rounding (wide mode keeps Bq = (B' + 32768) - 32768 itself)
+            const float Bm = __fadd_rn(m, c_r);
+            return make_float2(a, wide ? __fsub_rn(Bm, SAMPLE_MAGIC) : Bm);
+        } else {
+            // (a, m) = (level_mean, level_stdv); src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
+            const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)a, p.digitisation), p.range), off_d);
+            return make_float2(0.f, __uint_as_float(to_i16_bits(v)));
+        }
+    };
+    const uint32_t par_w = map_off + W_PAR + 8 * (uint32_t)(t.nreg + m0);
+    if (m0 < nk_tile) {
+        if (SINGLE) {
+            if (NOISY) {   // METH: table of (A', M)
+#pragma unroll
+                for (int j = 0; j < 8; j++) *reinterpret_cast<float2 *>(smem + par_w + 8 * j) = make_par(mv[j].x, mv[j].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) *reinterpret_cast<float2 *>(smem + par_w + 8 * j) = make_par(mv[j].x, mv[j].y);
+            }
+        } else if ((t.nreg & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 pa = make_par(mv4[j].x, mv4[j].y), pb = make_par(mv4[j].z, mv4[j].w);
+                const int piece = QUAD ? j : ((j + rot4) & 3);   // (the 256-bit gathers arrive in k-mer order)
+                *reinterpret_cast<float4 *>(smem + par_w + 16 * piece) = make_float4(pa.x, pa.y, pb.x, pb.y);
+            }
+        } else {   // odd window position (a second segment behind an odd number of k-mers): 8-byte stores
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int piece = QUAD ? j : ((j + rot4) & 3);
+                *reinterpret_cast<float2 *>(smem + par_w + 16 * piece) = make_par(mv4[j].x, mv4[j].y);
+                *reinterpret_cast<float2 *>(smem + par_w + 16 * piece + 8) = make_par(mv4[j].z, mv4[j].w);
+            }
+        }
+    }
+    t.nreg += nk_tile;
+    __syncwarp();
+}
+
+// After a tile's groups have been emitted: move what the next groups still need to the front of the window.
+template <bool RAND_DWELL>
+__device__ __forceinline__ void slide_window(const GenParams &p, int lane, unsigned char *smem, uint32_t map_off, Run &t) {
+    const uint32_t gdone = (8 * t.cur_c - t.fmap) >> 8;   // whole groups emitted since the map's origin
+    if (gdone == 0) return;
+    const uint32_t fmap2 = t.fmap + GROUP_S * gdone;
+    int32_t kt;       // first k-mer still needed (kept even: parameter stores are 16 bytes wide)
+    int32_t n_ent = 0;
+    const uint32_t e_sh = 8 * gdone;
+    if (RAND_DWELL) {
+        if (t.f_end <= fmap2) {
+            kt = t.nreg;
+        } else {
+            const uint2 ent = *reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * e_sh);
+            kt = (int32_t)(ent.y + (ent.x & 1u));
+            n_ent = (int32_t)((t.f_end - 1 - t.fmap) >> 5) - (int32_t)e_sh + 1;
+        }
+    } else {
+        const int32_t d = (int32_t)fmap2 - t.fix_f0;
+        kt = d > 0 ? (int32_t)div_sps(p, (uint32_t)d) : 0;
+        kt = min(kt, t.nreg);
+    }
+    kt &= ~1;
+    __syncwarp();
+    if (kt > 0) {
+        const int32_t n = t.nreg - kt;
+        for (int32_t i0 = 0; i0 < n; i0 += 128) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int32_t i = i0 + lane + 32 * u;
+                if (i < n) v[u] = *reinterpret_cast<const float2 *>(smem + map_off + W_PAR + 8 * (kt + i));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int32_t i = i0 + lane + 32 * u;
+                if (i < n) *reinterpret_cast<float2 *>(smem + map_off + W_PAR + 8 * i) = v[u];
+            }
+            __syncwarp();
+        }
+    }
+    if (RAND_DWELL) {
+        // entries [e_sh, e_sh + n_ent) -> [0, n_ent), bases re-indexed; everything behind them cleared
+        uint2 ent = make_uint2(0u, 0u);
+        if (lane < n_ent) ent = *reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * (e_sh + lane));
+        __syncwarp();
+        for (int32_t x = lane; x < MAP_ENT + 2; x += 32) {
+            uint2 w = make_uint2(0u, 0u);
+            if (x < n_ent) w = make_uint2(ent.x, ent.y - (uint32_t)kt);   // (n_ent <= 10: a group and the entry after it)
+            *reinterpret_cast<uint2 *>(smem + map_off + W_MAP + 8 * x) = w;
+        }
+        t.last_e = max(t.last_e - (int32_t)e_sh, -1);
+    } else {
+        t.fix_f0 += kt * p.sps_fixed;
+    }
+    t.nreg -= kt;
+    t.fmap = fmap2;
+    __syncwarp();
+}
+
+// A tile with more samples than the window holds (T is chosen so that this takes a six-sigma run of long dwells): every
+// lane walks k-mers of its own and stores sample by sample.  Unconditionally correct, never fast.
+__device__ __forceinline__ uint32_t draw_word_dyn(const uint4 &w, uint32_t j) {
+    const uint32_t x = (j >> 1) == 0 ? w.x : (j >> 1) == 1 ? w.y : (j >> 1) == 2 ? w.z : w.w;
+    return (j & 1u) ? __byte_perm(x, x, 0x1032) : x;
+}
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
+__device__ __noinline__ void slow_tile(const GenParams &p, const unsigned char *smem, int lane, int tile, int64_t a_off, int64_t b_off,
+                                       int32_t a_rem, int32_t nk, uint32_t B, uint32_t S, uint32_t L, int16_t *out, double offset,
+                                       uint32_t r_lo, uint32_t r_hi) {
+    const RngKey key{p.key0, p.key1, r_lo, r_hi};
+    const uint32_t hmul = amp_hmul(r_lo);
+    const float c_r = __fsub_rn(SAMPLE_MAGIC, (float)offset);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(p.kpos + (size_t)tile * (TK / 8));
+    for (int m = lane; m < nk; m += 32) {
+        uint32_t rank = 0;
+        for (int i = 0; i < p.k; i++) {
+            const int pos = m + i;
+            const uint8_t c = base_code(p.bases[(pos < a_rem ? a_off : b_off) + pos]);
+            rank = METH ? rank * 5 + (c >> 4) : (rank << 2) | (c & 3);
+        }
+        uint32_t start, d;
+        if (RAND_DWELL) {
+            start = row[m];
+            d = (m + 1 < nk ? (uint32_t)row[m + 1] : S) - start;
+        } else {
+            start = (uint32_t)m * (uint32_t)p.sps_fixed;
+            d = (uint32_t)p.sps_fixed;
+        }
+        float A = 0.f, Bq = 0.f;
+        uint32_t fixed_v = 0;
+        if (NOISY) {
+            const float2 am = p.model_am[rank];
+            A = am.x;
+            Bq = __fsub_rn(__fadd_rn(am.y, c_r), SAMPLE_MAGIC);
+        } else {
+            fixed_v = to_i16_bits(__dsub_rn(__ddiv_rn(__dmul_rn((double)p.model[rank].x, p.digitisation), p.range), offset));
+        }
+        for (uint32_t s = 0; s < d; s++) {
+            const uint32_t n = B + start + s;
+            const uint32_t q = REV ? L - 1 - n : n;
+            uint32_t v = fixed_v;
+            if (NOISY) {
+                const uint32_t Cq = q >> 3;
+                const uint4 r4 = philox4x32_rk(Cq, r_lo, r_hi, ST_AMP, p.rk);
+                const uint32_t off = z_offset(draw_word_dyn(r4, q & 7u), amp_class4(Cq, hmul));
+                float z = *reinterpret_cast<const float *>(smem + SM_Z + off);
+                if (z_is_tail(off)) z = z_tail(p.z2, off, q, key, ST_AMP_TAIL);
+                v = sample_exact(z, A, Bq);
+            }
+            out[q] = (int16_t)v;
+        }
+    }
+}
+
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
+__global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
+    constexpr bool USE_Z = NOISY;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    unsigned long long *stage_bar = reinterpret_cast<unsigned long long *>(smem + SM_MBAR);
+    const uint32_t map_off = SM_WARP + (uint32_t)warp * WARP_BYTES;
+    const uint32_t wbase = opaque_smem_addr(smem + map_off);  // this warp's buffer, for the asynchronous copies
+
+    // ---- this warp's range of tiles; its first descriptor ----
+    const int64_t gwarp = (int64_t)blockIdx.x * K4_WARPS + warp, nwarp = (int64_t)gridDim.x * K4_WARPS;
+    const int lo = (int)(((int64_t)p.n_tiles * gwarp) / nwarp), hi = (int)(((int64_t)p.n_tiles * (gwarp + 1)) / nwarp);
+    const bool has_work = lo < hi;
+    if (has_work) {
+        fetch_tile_desc(p, wbase, W_DESC, lo, lane);
+        cp_async_commit();
+    }
+    // ---- prologue: tables ----
+    if (smem_u32(smem) != SMEM_ORIGIN) __trap();  // lds_f32 & co. address shared memory absolutely (the host checks this too)
+    if (tid == 0) mbar_init(stage_bar, 1);
+    for (int i = tid; i < 256; i += K4_THREADS) smem[SM_CODE + i] = base_code(i);
+    __syncthreads();
+    if (USE_Z) {
+        if (tid == 0) {
+            mbar_expect_tx(stage_bar, Z32_BYTES);
+            tma_load_1d(smem + SM_Z, p.z32, Z32_BYTES / 2, stage_bar);  // two 64 KB bulk copies
+            tma_load_1d(smem + SM_Z + Z32_BYTES / 2, reinterpret_cast<const unsigned char *>(p.z32) + Z32_BYTES / 2, Z32_BYTES / 2, stage_bar);
+        }
+        mbar_wait(stage_bar, 0);
+    }
+    if (!has_work) return;
+    cp_async_wait_all();
+    __syncwarp();
+    fetch_tile_inputs<RAND_DWELL>(p, smem, wbase, map_off + W_DESC, W_RD, lo, lane);
+    fetch_tile_desc(p, wbase, W_DESC + 48, min(lo + 1, p.n_tiles - 1), lane);
+    cp_async_commit();
+
+    LaneC lc;
+    lc.lw = REV ? 31u - (uint32_t)lane : (uint32_t)lane;
+    lc.ent_sh = 8u * (lc.lw & 3u);
+    lc.ent_lane = 8u * (lc.lw >> 2);
+    lc.lane4 = (uint32_t)lane << 2;
+
+    Run t;
+    bool active = false;
+    const uint32_t r0_lo = (uint32_t)(uint64_t)p.first_read, r0_hi = (uint32_t)((uint64_t)p.first_read >> 32);
+
+    // ---- main loop: this warp's tiles; the inputs of tile i+1 and the descriptor of tile i+2 fly while tile i's samples are emitted ----
+    uint32_t slot = 0;
+    for (int tile = lo; tile < hi; tile++, slot ^= 1) {
+        cp_async_wait_all();
+        __syncwarp();
+        const uint32_t desc_off = map_off + W_DESC + slot * 48, rd_off = map_off + W_RD + slot * 32;
+        const uint4 d0 = *reinterpret_cast<const uint4 *>(smem + desc_off);
+        const uint4 d1 = *reinterpret_cast<const uint4 *>(smem + desc_off + 16);
+        const uint4 d2 = *reinterpret_cast<const uint4 *>(smem + desc_off + 32);
+        TileIn td;
+        td.a_off = (int64_t)(((uint64_t)d0.y << 32) | d0.x);
+        td.b_off = (int64_t)(((uint64_t)d0.w << 32) | d0.z);
+        td.a_rem = (int32_t)d1.x;
+        td.nk = (int32_t)(d1.y & 0xFFFFu);
+        td.S = d2.w;
+        const uint32_t flags = d1.y >> 16;
+        const int32_t read = (int32_t)d1.z;
+        const uint32_t B = d2.z;
+        const bool rfirst = (flags & TILE_READ_FIRST) != 0, rlast = (flags & TILE_READ_LAST) != 0;
+        const bool last = rlast || tile == hi - 1;
+        auto prefetch_next = [&]() {
+            __syncwarp();   // (every lane is done with this tile's base window and prefix row)
+            if (tile + 1 < hi) {
+                fetch_tile_inputs<RAND_DWELL>(p, smem, wbase, map_off + W_DESC + (slot ^ 1) * 48, W_RD + (slot ^ 1) * 32, tile + 1, lane);
+                fetch_tile_desc(p, wbase, W_DESC + slot * 48, min(tile + 2, p.n_tiles - 1), lane);
+                cp_async_commit();
+            }
+        };
+
+        // ---- does the tile fit behind what the window still holds?  (else the run is cut here: the group in progress is
+        // finished by the exact path on both sides of the cut, exactly like a range boundary) ----
+        if (active) {
+            bool fits = t.nreg + td.nk <= p.par_cap;
+            if (RAND_DWELL) fits = fits && ((t.f_end - t.fmap + td.S + 31) >> 5) + 2 <= (uint32_t)MAP_ENT;
+            if (!fits || td.S > p.tile_s_cap) {
+                emit_ready<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, true, t.f_end);
+                active = false;
+            }
+        }
+        if (!active) {
+            // ---- a run begins: the read's constants, the frame, an empty window ----
+            const int64_t sigoff = *reinterpret_cast<const int64_t *>(smem + rd_off);
+            t.L = *reinterpret_cast<const uint32_t *>(smem + rd_off + 8);
+            t.offset = *reinterpret_cast<const double *>(smem + rd_off + 16);
+            t.out = p.sig + sigoff;
+            t.c_r = __fsub_rn(SAMPLE_MAGIC, (float)t.offset);
+            const uint64_t rg = (((uint64_t)r0_hi << 32) | r0_lo) + (uint64_t)(int64_t)read;
+            t.r_lo = (uint32_t)rg; t.r_hi = (uint32_t)(rg >> 32);
+            t.hmul = amp_hmul(t.r_lo);
+        }
+        if (td.S > p.tile_s_cap) {
+            slow_tile<NOISY, RAND_DWELL, METH, REV>(p, smem, lane, tile, td.a_off, td.b_off, td.a_rem, td.nk, B, td.S, t.L, t.out, t.offset, t.r_lo, t.r_hi);
+            prefetch_next();
+            continue;
+        }
+        if (!active) {
+            const uint32_t delta = REV ? ((GROUP_S - ((t.L - B) & (GROUP_S - 1))) & (GROUP_S - 1)) : (B & (GROUP_S - 1));
+            t.C0 = REV ? ((t.L - B + delta) >> 3) - 1u : (B - delta) >> 3;
+            // a run that does not start its read starts where another warp's range (or a slow tile) ended: exactly there
+            t.clip_lo = (rfirst) ? 0u : delta;
+            t.f_end = delta;
+            t.fmap = 0;
+            t.cur_c = delta >> 3;
+            t.nreg = 0;
+            t.last_e = -1;
+            t.fix_f0 = (int32_t)delta;
+            if (RAND_DWELL)
+                for (int32_t x = lane; x < MAP_ENT + 2; x += 32) *reinterpret_cast<uint2 *>(smem + map_off + W_MAP + 8 * x) = make_uint2(0u, 0xFFFFFFFFu);
+            if (lane == 0) *reinterpret_cast<float2 *>(smem + map_off + W_PARG + 8) = make_float2(0.f, NOISY ? SAMPLE_MAGIC : 0.f);
+            active = true;
+            __syncwarp();
+        }
+        register_tile<NOISY, RAND_DWELL, METH, REV, QUAD && !METH>(p, lane, smem, map_off, t, td);
+        prefetch_next();
+        t.f_end += td.S;
+        emit_ready<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, last, rlast ? 0xFFFFFFFFu : t.f_end);
+        if (last) active = false;
+        else slide_window<RAND_DWELL>(p, lane, smem, map_off, t);
+    }
+}
+
+}  // namespace sqg
