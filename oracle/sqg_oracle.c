@@ -423,16 +423,30 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
             volatile float Bm = M + c_r;
             const float Bq = Bm - 32768.0f;
             for (int j = 0; j < sps[i]; j++, n++) {
-                /* Philox draws are addressed by the position in the EMITTED signal (after the RNA reversal of
-                 * src/gensig.c:348-354), eight 10-bit draws per block.  The draw's table class is the block's low five
-                 * bits XOR five hash bits of (block >> 5, read): a bijection of the 32 blocks of a group, different from
-                 * group to group, so no sample position is tied to one class. */
+                /* Philox draws are addressed by the position q in the EMITTED signal (after the RNA reversal of
+                 * src/gensig.c:348-354).  A block holds twelve 10-bit draws - three fields per word: bits 7..16 (F0), bits
+                 * 17..26 (F1), bits 27..31,0..4 (F2) - and the chunks of 8 samples are taken in units of 96: chunk
+                 * Cq = 96 u + 32 g + l uses blocks A = 64 u + 2 l and B = A + 1:
+                 *   g = 0: sample e -> word e/2 of A, F0 (e even) / F1 (e odd);   g = 2: the same of B;
+                 *   g = 1: F2 of word e of A (e < 4) or of word e - 4 of B.
+                 * The draw's table class is l XOR five hash bits of (Cq >> 5, read): a bijection of the 32 chunks of a
+                 * group, different from group to group, so no sample position is tied to one class. */
                 uint32_t q = (uint32_t)(rna ? total - 1 - n : n);
-                uint32_t blk = q >> 3;
+                uint32_t Cq = q >> 3, e = q & 7;
+                uint32_t u = Cq / 96, r = Cq % 96, g = r >> 5, l = r & 31;
+                uint32_t blk = 64 * u + 2 * l + (g == 2 || (g == 1 && e >= 4) ? 1 : 0);
                 uint32_t ctr[4] = {blk, r_lo, r_hi, ST_AMP}, w[4];
                 philox(ctr, o->key, w);
-                uint32_t h = ((blk >> 5) * 0x9E3779B1u + r_lo * 0x85EBCA6Bu) >> 27;
-                float z = sqo_z32(o->zt, zindex(w, q & 7, (blk & 31u) ^ h), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
+                uint32_t d10;
+                if (g == 1) {
+                    uint32_t x = w[e & 3];
+                    d10 = ((x >> 27) | (x << 5)) & 0x3FFu; /* bits 27..31 (low part of the draw), 0..4 (high part) */
+                } else {
+                    uint32_t x = w[e >> 1];
+                    d10 = (e & 1) ? (x >> 17) & 0x3FFu : (x >> 7) & 0x3FFu;
+                }
+                uint32_t h = ((Cq >> 5) * 0x9E3779B1u + r_lo * 0x85EBCA6Bu) >> 27;
+                float z = sqo_z32(o->zt, (d10 << 5) | (l ^ h), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
                 raw[n] = to_i16_f(fma_rz(z, A, Bq));
             }
         }

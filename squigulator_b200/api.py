@@ -138,7 +138,7 @@ class SignalGenerator:
     """One sqg_ctx_t: what init_core()/init_rand() set up for the hot path (reference src/sim.c:215-326)."""
 
     def __init__(self, profile, model, kmer_size, flags=0, seed=1, meth=False, amp_noise=1.0, rng_mode=RNG_PHILOX,
-                 device=0, n_slots=0, device_model_ptr=None):
+                 device=0, n_slots=0, device_model_ptr=None, tuning=0):
         self.lib = load_library()
         if isinstance(profile, str):
             d, f = PROFILES[profile]
@@ -147,7 +147,7 @@ class SignalGenerator:
             profile = Profile.from_dict(profile)
         num_kmer = (5 if meth else 4) ** kmer_size
         self.cfg = Config(profile, flags & 0xFFFFFFFF, kmer_size, num_kmer, 1 if meth else 0, amp_noise, seed, rng_mode,
-                          device, n_slots, 0)
+                          device, n_slots, tuning)
         self.h = C.c_void_p()
         if device_model_ptr is not None:
             rc = self.lib.sqg_init_device_model(C.byref(self.h), C.byref(self.cfg), C.c_void_p(device_model_ptr))

@@ -110,6 +110,7 @@ struct Slot {
     DevBuf<uint32_t> d_tile_sum, d_siglen, d_n0;
     DevBuf<uint4> d_kpos;  // TK uint16 per tile: prefix of the dwells within the tile (K1 -> K4)
     DevBuf<int64_t> d_sigoff, d_meta;
+    DevBuf<ReadRec> d_read_rec;
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
     DevBuf<int32_t> d_ss;
@@ -153,7 +154,7 @@ struct Slot {
     bool const_written = false;
     void release() {
         d_bases.release(); d_segs.release(); d_reads.release(); d_tiles.release(); d_tile_sum.release(); d_kpos.release();
-        d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release();
+        d_siglen.release(); d_n0.release(); d_sigoff.release(); d_meta.release(); d_read_rec.release();
         d_offset.release(); d_median.release(); d_sig.release(); d_ss.release();
         d_rank.release(); d_rank_sorted.release(); d_idx.release(); d_idx_sorted.release(); d_dsorted.release();
         d_excl.release(); d_heads.release(); d_segstart.release(); d_cpos.release(); d_cub.release();
@@ -418,6 +419,7 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     CU(s.d_siglen.ensure(nr, false, s.stream));
     CU(s.d_n0.ensure(nr, false, s.stream));
     CU(s.d_sigoff.ensure(nr, false, s.stream));
+    CU(s.d_read_rec.ensure(nr, false, s.stream));
     CU(s.d_offset.ensure(nr, false, s.stream));
     CU(s.d_median.ensure(nr, false, s.stream));
     CU(s.d_meta.ensure(4, false, s.stream));
@@ -487,7 +489,7 @@ GenParams slot_params(sqg_ctx *ctx, Slot &s) {
     GenParams p = ctx->base;
     p.bases = s.d_bases.p; p.segs = s.d_segs.p; p.reads = s.d_reads.p;
     p.tiles = s.d_tiles.p; p.tile_sum = s.d_tile_sum.p; p.kpos = s.d_kpos.p;
-    p.read_siglen = s.d_siglen.p; p.read_n0 = s.d_n0.p; p.read_sigoff = s.d_sigoff.p;
+    p.read_siglen = s.d_siglen.p; p.read_n0 = s.d_n0.p; p.read_sigoff = s.d_sigoff.p; p.read_rec = s.d_read_rec.p;
     p.read_offset = s.d_offset.p; p.read_median = s.d_median.p; p.meta = s.d_meta.p;
     p.sig = s.d_sig.p; p.ss = s.d_ss.p;
     p.n_reads = (int32_t)s.n_reads; p.n_segs = (int32_t)s.n_segs; p.n_tiles = (int32_t)s.n_tiles;
@@ -844,10 +846,13 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
         const double mx = std::floor((double)b.dwell_mean + (double)Z_MAX * (double)b.dwell_std + 0.5) + 2.0;
         if (!(mx < 1200.0)) return fail(ctx, SQG_ERR_ARG, "dwell_mean + 6.06*dwell_std too large for one tile");
         // k-mers per tile: as many as keep a tile's samples inside the signal kernel's window even for a six-sigma run of
-        // long dwells (mean of the folded normal <= mean + std); a tile beyond TILE_S_CAP would still be generated
+        // long dwells; a tile beyond TILE_S_CAP would still be generated
         // correctly, by that kernel's slow path.  T * mx < 2^16: the dwell kernel stores 16-bit prefixes.
         int T = TK;
-        const double dm = (double)b.dwell_mean + (double)b.dwell_std, ds = (double)b.dwell_std;
+        // moments of the folded normal |N(mean, std)| (the fold of draws below 1 moves them by one sample at most)
+        const double mu = (double)b.dwell_mean, sg = (double)b.dwell_std;
+        const double dm = sg * std::sqrt(2.0 / M_PI) * std::exp(-mu * mu / (2 * sg * sg)) + mu * std::erf(mu / (sg * std::sqrt(2.0))) + 1.0;
+        const double ds = std::sqrt(std::max(mu * mu + sg * sg - (dm - 1.0) * (dm - 1.0), 0.0));
         while (T > 8 && (T * dm + 6.0 * ds * std::sqrt((double)T) > (double)TILE_S_CAP || T * mx >= 65000.0)) T -= 8;
         b.T = T;
         b.tile_s_cap = TILE_S_CAP;

@@ -56,6 +56,16 @@ struct __align__(16) TileDesc {
 };
 static_assert(sizeof(TileDesc) == 48, "TileDesc is loaded as three 16-byte words");
 
+// what the signal kernel needs to know about a read, in one 32-byte record (K3)
+struct __align__(16) ReadRec {
+    int64_t sigoff;   // start of the read in the signal arena
+    uint32_t L;       // samples in the read
+    uint32_t pad0;
+    double offset;    // ADC offset
+    uint64_t pad1;
+};
+static_assert(sizeof(ReadRec) == 32, "ReadRec is fetched as two 16-byte words");
+
 struct GenParams {
     // inputs
     const uint8_t *bases;
@@ -74,6 +84,7 @@ struct GenParams {
     uint32_t *read_siglen;
     uint32_t *read_n0;
     int64_t *read_sigoff;
+    ReadRec *read_rec;
     double *read_offset;
     double *read_median;
     int64_t *meta;  // [0] arena samples needed, [1] sum of siglen, [2] error flag
@@ -372,8 +383,12 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
     __syncthreads();
     uint64_t base = s_warp[tid >> 5] + inc - part;
     for (int r = lo; r < hi; r++) {
+        const uint32_t l = p.read_siglen[r];
         p.read_sigoff[r] = (int64_t)base;
-        base += ((uint64_t)p.read_siglen[r] + 63) & ~63ull;
+        ReadRec rr;
+        rr.sigoff = (int64_t)base; rr.L = l; rr.pad0 = 0; rr.offset = p.read_offset[r]; rr.pad1 = 0;
+        p.read_rec[r] = rr;
+        base += ((uint64_t)l + 63) & ~63ull;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, o);

@@ -32,10 +32,18 @@ namespace sqg {
 constexpr int K4_WARPS = SQG_K4_WARPS;
 constexpr int K4_THREADS = K4_WARPS * 32;  // register budget: 65536 / 512 = 128
 constexpr uint32_t GROUP_S = 256;          // samples per group: 32 lanes x 8
-constexpr int PAR_TAIL = 128;              // k-mers carried from tile to tile at most (else the run is cut)
+constexpr uint32_t UNIT_G = 3;             // groups per unit: 96 chunks share 64 Philox blocks (12 draws each)
+constexpr uint32_t UNIT_C = 32 * UNIT_G, UNIT_S = GROUP_S * UNIT_G;
+#ifndef SQG_PAR_TAIL
+#define SQG_PAR_TAIL 128
+#endif
+#ifndef SQG_MAP_ENT
+#define SQG_MAP_ENT 168
+#endif
+constexpr int PAR_TAIL = SQG_PAR_TAIL;     // k-mers carried from tile to tile at most (else the run is cut)
 constexpr int PAR_N = TK + PAR_TAIL;       // registered k-mers at most
-constexpr int MAP_ENT = 168;               // map entries (32 samples each): window of 5376 samples
-constexpr uint32_t TILE_S_CAP = MAP_ENT * 32 - GROUP_S - 64;   // samples of one tile the window is guaranteed to hold
+constexpr int MAP_ENT = SQG_MAP_ENT;       // map entries (32 samples each): 168 = a window of 5376 samples
+constexpr uint32_t TILE_S_CAP = (MAP_ENT - 8) * 32 - UNIT_S - 32;   // samples of one tile the window is guaranteed to hold
 constexpr int DIG_BYTES = TK + 32;         // digits of the tile's base window; the same size holds the raw window (16-byte granules)
 // per-warp buffer
 constexpr uint32_t W_MAP = 0;                               // MAP_ENT (+2 that the one-ahead loads may touch) x {bits, base}
@@ -55,7 +63,7 @@ constexpr uint32_t SM_TOTAL = SM_WARP + K4_WARPS * WARP_BYTES;
 static_assert(SM_WARP % 16 == 0 && WARP_BYTES % 16 == 0 && W_PAR % 16 == 0 && W_RAW % 16 == 0 && W_DIG % 16 == 0 && W_PL % 16 == 0 &&
               W_DESC % 16 == 0 && W_RD % 16 == 0, "alignment");
 static_assert(SM_TOTAL <= 232448, "227 KB of shared memory per CTA");
-static_assert(PAR_N % 2 == 0 && TK == 256, "layout assumptions");
+static_assert(PAR_N % 2 == 0 && TK == 256 && MAP_ENT % 2 == 0, "layout assumptions");
 
 // ---- per-lane asynchronous global -> shared copies (SASS: LDGSTS) for the next tile's inputs ----
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
@@ -108,13 +116,49 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t off) {
     return v;
 }
 
-// ---- the amplitude draws.  The sample at position q of the EMITTED signal uses draw q & 7 of Philox
-// block q >> 3 (stream ST_AMP); its table CLASS is (block & 31) ^ h, h = five hash bits of the block's group of 32
-// (and of the read): within a group the classes are a bijection of the lanes - one bank per lane - and over the groups
-// every position of the signal meets every class.
+// ---- the amplitude draws.  A Philox block holds TWELVE 10-bit draws - three fields per word: bits
+// 7..16 (F0), bits 17..26 (F1), bits 27..31,0..4 (F2) - so two blocks serve three chunks.  The chunks (= 8 samples) of
+// the EMITTED signal are taken in UNITS of 96: chunk Cq = 96 u + 32 g + l (g = 0..2, l = 0..31) belongs to blocks
+// A = 64 u + 2 l and B = A + 1 (stream ST_AMP), and its sample e uses
+//   g = 0: word e/2 of A, field F0 (e even) or F1 (e odd)        g = 2: the same of B
+//   g = 1: field F2 of word e of A (e < 4) or of word e - 4 of B (e >= 4)
+// A lane of the signal kernel handles the three chunks l, 32 + l, 64 + l of a unit with two Philox calls.  The draw's
+// table CLASS is l ^ h, h = five hash bits of the chunk's group of 32 (and of the read): within a group the classes are a
+// bijection of the lanes - one bank per lane - and over the groups every position of the signal meets every class.
 __device__ __forceinline__ uint32_t amp_class_hash(uint32_t group, uint32_t hmul) { return (group * 0x9E3779B1u + hmul) >> 27; }
 __device__ __forceinline__ uint32_t amp_class4(uint32_t Cq, uint32_t hmul) { return ((Cq & 31u) ^ amp_class_hash(Cq >> 5, hmul)) << 2; }
 __device__ __forceinline__ uint32_t amp_hmul(uint32_t r_lo) { return r_lo * 0x85EBCA6Bu; }
+// a field moved to bits 7..16, where z_offset() masks it: F1 by a multiply-high (x >> 10 on the FMA pipe, which has
+// room; the ALU pipe does not), F2 by a rotation
+__device__ __forceinline__ uint32_t amp_f1(uint32_t x) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 4194304;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t amp_f2(uint32_t x) { return __funnelshift_r(x, x, 20); }
+template <int G>
+__device__ __forceinline__ void amp_fields(const uint4 &A, const uint4 &B, uint32_t (&dw)[8]) {
+    const uint32_t a[4] = {A.x, A.y, A.z, A.w}, b[4] = {B.x, B.y, B.z, B.w};
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        if (G == 1) dw[e] = amp_f2(e < 4 ? a[e] : b[e - 4]);
+        else {
+            const uint32_t x = G == 0 ? a[e >> 1] : b[e >> 1];
+            dw[e] = (e & 1) ? amp_f1(x) : x;
+        }
+    }
+}
+// any chunk, by itself (exact path, masked groups, slow tiles): one or two Philox calls
+__device__ __forceinline__ void amp_draws(const GenParams &p, uint32_t Cq, uint32_t r_lo, uint32_t r_hi, uint32_t (&dw)[8]) {
+    const uint32_t u = Cq / UNIT_C, r = Cq - u * UNIT_C, g = r >> 5;
+    const uint32_t blk = 64u * u + 2u * (r & 31u);
+    uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
+    if (g != 2) A = philox4x32_rk(blk, r_lo, r_hi, ST_AMP, p.rk);
+    if (g != 0) B = philox4x32_rk(blk + 1, r_lo, r_hi, ST_AMP, p.rk);
+    if (g == 0) amp_fields<0>(A, B, dw);
+    else if (g == 1) amp_fields<1>(A, B, dw);
+    else amp_fields<2>(A, B, dw);
+}
 
 // What a warp knows about the run it is in: consecutive tiles of one read, from where the warp's range (or the read)
 // begins to where it ends.  FRAME coordinates f count samples in generation order from a point <= the run's first
@@ -132,7 +176,6 @@ struct Run {
     uint32_t fmap;        // frame coordinate of map entry 0 (a multiple of 256)
     uint32_t cur_c;       // next frame chunk to emit
     int32_t nreg;         // k-mers in par[]
-    int32_t last_e;       // map entry holding the first sample of the last registered k-mer (-1: none, or before the map)
     int32_t fix_f0;       // fixed-dwell modes: frame coordinate of the first sample of par[0]'s k-mer
 };
 
@@ -168,10 +211,10 @@ __device__ __forceinline__ void chunk_kmers(const GenParams &p, const unsigned c
 // The exact path of one chunk, start to finish (rare: a chunk shared with another warp's range, a chunk with a flagged
 // sample - tail cell of the table, negative value, value beyond int16 - or with four or more k-mers, and every chunk in
 // wide mode): samples are trunc(fma.rz(z, A', Bq)) with the tail cells refined and any number of boundaries; only frame
-// samples in [clip_lo, clip_hi) are stored.  par[] holds B'+32768 (or Bq itself in wide mode).
+// samples in [clip_lo, clip_hi) are stored.
 template <bool NOISY, bool RAND_DWELL, bool REV>
 __device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char *smem, uint32_t map_off, uint32_t fmap, int32_t fix_f0,
-                                         uint32_t C0, uint32_t r_lo, uint32_t r_hi, uint32_t hmul, int16_t *out, uint32_t c,
+                                         uint32_t C0, uint32_t r_lo, uint32_t r_hi, uint32_t hmul, float c_r, int16_t *out, uint32_t c,
                                          uint32_t clip_lo, uint32_t clip_hi) {
     uint32_t k0, m1;
     chunk_kmers<RAND_DWELL>(p, smem, map_off, fmap, fix_f0, c, k0, m1);
@@ -179,9 +222,8 @@ __device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char
     const uint32_t Cq = REV ? C0 - c : C0 + c;
     const uint32_t class4 = amp_class4(Cq, hmul);
     const RngKey key{p.key0, p.key1, r_lo, r_hi};
-    uint4 r4 = make_uint4(0, 0, 0, 0);
-    if (NOISY) r4 = philox4x32_rk(Cq, r_lo, r_hi, ST_AMP, p.rk);
-    const float sub = p.wide ? 0.f : SAMPLE_MAGIC;
+    uint32_t dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (NOISY) amp_draws(p, Cq, r_lo, r_hi, dw);
     int16_t *dst = out + (size_t)Cq * 8;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
@@ -191,10 +233,10 @@ __device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char
             const float2 ab = *reinterpret_cast<const float2 *>(smem + par0 + 8 * __popc(m1 & ((2u << j) - 1u)));
             uint32_t v;
             if (NOISY) {
-                const uint32_t off = z_offset(draw_word(r4, e), class4);
+                const uint32_t off = z_offset(dw[e], class4);
                 float z = *reinterpret_cast<const float *>(smem + SM_Z + off);
                 if (z_is_tail(off)) z = z_tail(p.z2, off, Cq * 8 + e, key, ST_AMP_TAIL);
-                v = sample_exact(z, ab.x, __fsub_rn(ab.y, sub));
+                v = sample_exact(z, ab.x, __fsub_rn(__fadd_rn(ab.y, c_r), SAMPLE_MAGIC));   // par[] holds (A', M)
             } else {
                 v = __float_as_uint(ab.y);
             }
@@ -210,22 +252,23 @@ __device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char
 // FMA pipe, and no shared-memory traffic of its own.  Returns non-zero when the chunk has to be redone by the exact path
 // (flagged sample, 4+ k-mers).
 template <bool NOISY, bool REV>
-__device__ __forceinline__ uint32_t fast_chunk(const GenParams &p, uint32_t k0, uint32_t m1, uint32_t par_base, uint32_t Cq,
-                                               uint32_t class4, uint32_t r_lo, uint32_t r_hi, int16_t *out) {
+__device__ __forceinline__ uint32_t fast_chunk(uint32_t k0, uint32_t m1, uint32_t par_base, const uint32_t (&dw)[8], uint32_t class4, float c_r,
+                                               uint4 &pk) {
     const uint32_t par0 = k0 * 8 + par_base;
-    const float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0), q2 = lds_f2<16>(par0);
+    float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0), q2 = lds_f2<16>(par0);
+    if (NOISY) {   // par[] holds (A', M): B' + 32768 = M + c_r, one rounding
+        q0.y = __fadd_rn(q0.y, c_r); q1.y = __fadd_rn(q1.y, c_r); q2.y = __fadd_rn(q2.y, c_r);
+    }
     const uint32_t t1 = m1 - 1u;        // bit j clear  <=>  slot j lies at or after the 1st boundary
     const uint32_t m2 = m1 & t1;        // boundaries after the first
     const uint32_t t2 = m2 - 1u;        // bit j clear  <=>  slot j lies at or after the 2nd boundary
     const uint32_t m3 = m2 & t2;        // non-zero: a 3rd boundary -> exact path
-    uint4 pk;
     uint32_t bad;
     if (NOISY) {
-        const uint4 r4 = philox4x32_rk(Cq, r_lo, r_hi, ST_AMP, p.rk);
         float zz[8], v[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {   // e = slot in the emitted chunk = which draw; j = slot in generation order
-            zz[e] = lds_f32<SM_Z>(z_offset(draw_word(r4, e), class4));
+            zz[e] = lds_f32<SM_Z>(z_offset(dw[e], class4));
             v[e] = fma_rz(zz[e], q0.x, q0.y);
         }
 #pragma unroll
@@ -260,24 +303,16 @@ __device__ __forceinline__ uint32_t fast_chunk(const GenParams &p, uint32_t k0, 
                         __byte_perm(v[4], v[5], 0x5410), __byte_perm(v[6], v[7], 0x5410));
         bad = m3;
     }
-    st_cs_v4(out + (size_t)Cq * 8, pk);
     return bad;
 }
 
-// One group of 32 chunks.  FAST: all of them are whole and owned.  Otherwise only frame chunks [c_lo, c_hi) are emitted,
-// and those reaching outside [clip_lo, clip_hi) - or all of them when `all_exact` - take the exact path.
-template <bool NOISY, bool RAND_DWELL, bool REV, bool FAST>
-__device__ __forceinline__ void emit_group(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
-                                           uint32_t g, uint32_t c_lo, uint32_t c_hi, uint32_t clip_hi, bool all_exact) {
+// the chunk of this lane in frame group g: k-mers, class, samples from the draw words dw.  Returns the redo flag; the
+// caller stores pk.
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __forceinline__ uint32_t group_chunk(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
+                                                uint32_t g, const uint32_t (&dw)[8], uint32_t &Cq, uint4 &pk) {
     const uint32_t c = 32 * g + lc.lw;
-    const uint32_t Cq = REV ? t.C0 - c : t.C0 + c;
-    if (!FAST) {
-        if (c < c_lo || c >= c_hi) return;
-        if (all_exact || 8 * c < t.clip_lo || 8 * c + 8 > clip_hi) {
-            exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, map_off, t.fmap, t.fix_f0, t.C0, t.r_lo, t.r_hi, t.hmul, t.out, c, t.clip_lo, clip_hi);
-            return;
-        }
-    }
+    Cq = REV ? t.C0 - c : t.C0 + c;
     uint32_t k0, m1;
     if (RAND_DWELL) {
         const uint2 ent = lds_u2<W_MAP>(map_off + 64 * (g - (t.fmap >> 8)) + lc.ent_lane);
@@ -285,36 +320,95 @@ __device__ __forceinline__ void emit_group(const GenParams &p, const unsigned ch
     } else {
         chunk_kmers<false>(p, smem, map_off, t.fmap, t.fix_f0, c, k0, m1);
     }
-    // (Cq >> 5 is the same for all lanes of a group: groups are aligned in the emitted signal)
-    const uint32_t class4 = lc.lane4 ^ (amp_class_hash(Cq >> 5, t.hmul) << 2);
-    const uint32_t bad = fast_chunk<NOISY, REV>(p, k0, m1, map_off + W_PAR, Cq, class4, t.r_lo, t.r_hi, t.out);
-    if (__builtin_expect(bad != 0, 0))
-        exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, map_off, t.fmap, t.fix_f0, t.C0, t.r_lo, t.r_hi, t.hmul, t.out, c, 0u, 0xFFFFFFFFu);
+    // the emitted group of the chunk (the same for all lanes: groups are aligned in the emitted signal), computed from
+    // warp-uniform values so that the hash stays off the vector pipes
+    const uint32_t Gq = REV ? (t.C0 >> 5) - g : (t.C0 >> 5) + g;
+    const uint32_t class4 = lc.lane4 ^ (amp_class_hash(Gq, t.hmul) << 2);
+    return fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, pk);
 }
 
-// Emit what has become complete.  `last`: the run ends with the samples registered so far.
+// One group of 32 chunks by itself (where a run begins or ends): only frame chunks [c_lo, c_hi) are emitted, and those
+// reaching outside [clip_lo, clip_hi) - or all of them when `all_exact` - take the exact path.
 template <bool NOISY, bool RAND_DWELL, bool REV>
-__device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned char *smem, Run &t, const LaneC &lc, uint32_t map_off, bool last,
-                                           uint32_t clip_hi) {
+__device__ __forceinline__ void emit_group_single(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
+                                                  uint32_t g, uint32_t c_lo, uint32_t c_hi, uint32_t clip_hi, bool all_exact) {
+    const uint32_t c = 32 * g + lc.lw;
+    if (c < c_lo || c >= c_hi) return;
+    uint32_t lo = t.clip_lo, hi = clip_hi;
+    bool redo = all_exact || 8 * c < t.clip_lo || 8 * c + 8 > clip_hi;
+    if (!redo) {
+        uint32_t Cq, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint4 pk;
+        if (NOISY) amp_draws(p, REV ? t.C0 - c : t.C0 + c, t.r_lo, t.r_hi, dw);
+        redo = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, g, dw, Cq, pk) != 0;
+        st_cs_v4(t.out + (size_t)Cq * 8, pk);
+        lo = 0u; hi = 0xFFFFFFFFu;
+    }
+    if (redo) exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, map_off, t.fmap, t.fix_f0, t.C0, t.r_lo, t.r_hi, t.hmul, t.c_r, t.out, c, lo, hi);
+}
+
+// One whole unit: frame groups 3 uf .. 3 uf + 2.  Three independent chunks per lane from two Philox blocks, one check for
+// the rare redo behind them.
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
+                                               uint32_t uf, int lane) {
+    uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
+    if (NOISY) {
+        // emitted unit (warp-uniform: frame units are aligned with those of the emitted signal)
+        const uint32_t u = REV ? (t.C0 / UNIT_C) - uf : (t.C0 / UNIT_C) + uf;
+        const uint32_t blk = 64u * u + 2u * (uint32_t)lane;
+        A = philox4x32_rk(blk, t.r_lo, t.r_hi, ST_AMP, p.rk);
+        B = philox4x32_rk(blk + 1, t.r_lo, t.r_hi, ST_AMP, p.rk);
+    }
+    uint32_t Cq[3], bad[3], dw[8];
+    uint4 pk[3];
+    // frame order = emitted order (reversed reads: the unit's chunks come last group first)
+    amp_fields<REV ? 2 : 0>(A, B, dw);
+    bad[0] = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, 3 * uf, dw, Cq[0], pk[0]);
+    amp_fields<1>(A, B, dw);
+    bad[1] = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, 3 * uf + 1, dw, Cq[1], pk[1]);
+    amp_fields<REV ? 0 : 2>(A, B, dw);
+    bad[2] = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, 3 * uf + 2, dw, Cq[2], pk[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#ifdef SQG_KO_STORE
+        if (pk[i].x == 0x12345678u && pk[i].y == 0x9abcdef0u)
+#endif
+        st_cs_v4(t.out + (size_t)Cq[i] * 8, pk[i]);
+    }
+    if (__builtin_expect((bad[0] | bad[1] | bad[2]) != 0, 0)) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (bad[i])
+                exact_chunk<NOISY, RAND_DWELL, REV>(p, smem, map_off, t.fmap, t.fix_f0, t.C0, t.r_lo, t.r_hi, t.hmul, t.c_r, t.out, 32 * (3 * uf + i) + lc.lw, 0u, 0xFFFFFFFFu);
+    }
+}
+
+// Emit what has become complete: whole units by the fast path; where a run begins (up to its first unit boundary) and
+// where it ends, single groups.  `last`: the run ends with the samples registered so far.
+template <bool NOISY, bool RAND_DWELL, bool REV>
+__device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned char *smem, Run &t, const LaneC &lc, uint32_t map_off, int lane,
+                                           bool last, uint32_t clip_hi) {
     const uint32_t hi_c = last ? (t.f_end + 7) >> 3 : t.f_end >> 3;   // chunks below hi_c can be computed
     const bool all_exact = NOISY && p.wide;
+#ifdef SQG_KO_EMIT
+    if (t.f_end != 0x7FFFFFFFu) { t.cur_c = last ? hi_c : (hi_c / UNIT_C) * UNIT_C; return; }
+#endif
     while (t.cur_c < hi_c) {
-        const uint32_t g = t.cur_c >> 5;
-        if (!all_exact && (t.cur_c & 31u) == 0 && 8 * t.cur_c >= t.clip_lo) {
-            // whole groups: [g, g_end)
-            const uint32_t lim = min(hi_c, clip_hi >> 3);
-            const uint32_t g_end = lim >> 5;
-            if (g < g_end) {
-#pragma unroll 2
-                for (uint32_t gg = g; gg < g_end; gg++) emit_group<NOISY, RAND_DWELL, REV, true>(p, smem, t, lc, map_off, gg, 0, 0, 0, false);
-                t.cur_c = 32 * g_end;
+        if (!all_exact && t.cur_c % UNIT_C == 0 && 8 * t.cur_c >= t.clip_lo) {
+            uint32_t uf = t.cur_c / UNIT_C;
+            const uint32_t u_end = min(hi_c, clip_hi >> 3) / UNIT_C;   // whole units: [uf, u_end)
+            if (uf < u_end) {
+                for (; uf < u_end; uf++) emit_unit_fast<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, uf, lane);
+                t.cur_c = UNIT_C * u_end;
                 continue;
             }
+            if (!last) break;   // the unit completes with the next tile
         }
-        const uint32_t gend_c = 32 * (g + 1);
+        const uint32_t g = t.cur_c >> 5, gend_c = 32 * (g + 1);
         if (!last && gend_c > hi_c) break;   // the group completes with the next tile
         const uint32_t ce = min(gend_c, hi_c);
-        emit_group<NOISY, RAND_DWELL, REV, false>(p, smem, t, lc, map_off, g, t.cur_c, ce, clip_hi, all_exact);
+        emit_group_single<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, g, t.cur_c, ce, clip_hi, all_exact);
         t.cur_c = ce;
     }
 }
@@ -329,7 +423,7 @@ __device__ __forceinline__ bool tile_is_junction(const GenParams &p, int32_t a_r
 }
 
 // Asynchronous fetch of a tile's inputs into the warp's buffer: the base window as 16-byte granules (the aligned
-// superset of the window), its prefix row, its read's arena offset / length / ADC offset.  `desc_off` = the tile's
+// superset of the window), its prefix row, its read's record (arena offset, length, ADC offset).  `desc_off` = the tile's
 // descriptor, already in shared memory.
 template <bool RAND_DWELL>
 __device__ __forceinline__ void fetch_tile_inputs(const GenParams &p, const unsigned char *smem, uint32_t wbase, uint32_t desc_off,
@@ -345,9 +439,7 @@ __device__ __forceinline__ void fetch_tile_inputs(const GenParams &p, const unsi
         if ((uint32_t)lane * 16 < nbytes) cp_async16(wbase + W_RAW + lane * 16, g - shift + lane * 16);
     }
     if (RAND_DWELL) cp_async16(wbase + W_PL + lane * 16, p.kpos + (size_t)tile * (TK / 8) + lane);
-    if (lane == 0) cp_async8(wbase + rd_rel, p.read_sigoff + read);
-    if (lane == 1) cp_async4(wbase + rd_rel + 8, p.read_siglen + read);
-    if (lane == 2) cp_async8(wbase + rd_rel + 16, p.read_offset + read);
+    if (lane < 2) cp_async16(wbase + rd_rel + lane * 16, reinterpret_cast<const uint4 *>(p.read_rec + read) + lane);
 }
 __device__ __forceinline__ void fetch_tile_desc(const GenParams &p, uint32_t wbase, uint32_t desc_rel, int tile, int lane) {
     if (lane < 3) cp_async16(wbase + desc_rel + lane * 16, reinterpret_cast<const uint4 *>(p.tiles + tile) + lane);
@@ -362,7 +454,8 @@ struct TileIn {   // the descriptor fields phase A works from (warp-uniform)
 // Phase A of one tile: its k-mers are appended to the run's window.  Descriptor, base window and prefix row are already
 // in the warp's buffer.
 template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
-__device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsigned char *smem, uint32_t map_off, Run &t, const TileIn &td) {
+__device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsigned char *smem, uint32_t map_off, uint32_t wbase, Run &t,
+                                              const TileIn &td) {
     constexpr bool SINGLE = METH || !NOISY;   // one gather per k-mer from a table indexed by rank
     const int nk_tile = td.nk;
     const int nb = nk_tile + p.k - 1;
@@ -443,53 +536,39 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
         __syncwarp();   // (the digit buffer is rewritten by this warp's next tile)
     }
 
-    // (1b) the table gathers of this lane are issued now, so that their L2 latency runs under the shared-memory work of
-    // step (2).  Base-4 models: 16 two-bit digits packed first-digit-most-significant
+    // (1b) the table gathers of this lane.  Noisy modes: asynchronous copies (LDGSTS) from the (A', M) tables STRAIGHT INTO
+    // the window - no registers, no stores of our own, and a random-line gather costs the load/store unit far less this way
+    // than as LDG (measured: 0.17 ms instead of 0.42 ms per 2.1 G samples); the read's constant c_r is added where the
+    // samples are made.  Base-4 models: 16 two-bit digits packed first-digit-most-significant
     // (((w & 0x03030303) * 0x40100401) >> 24 packs 4 bytes); k-mers 2j, 2j+1 of the lane = the two k-mers of the
-    // (k+1)-mer at digit 2j: ONE 16-byte gather for both.  The four pairs are visited in ROTATED order
-    // jj(j) = (j + lane/2) & 3 so that the 16-byte parameter stores of a quarter-warp fall into 8 different bank groups.
-    float4 mv4[4];
+    // (k+1)-mer at digit 2j: ONE 16-byte gather for both.  Ideal-amplitude modes: the raw table into registers (double
+    // arithmetic below).
     float2 mv[8];
-    const int rot4 = lane >> 1;
+    const uint32_t par_w = map_off + W_PAR + 8 * (uint32_t)(t.nreg + m0);
+    const uint32_t par_a = wbase + W_PAR + 8 * (uint32_t)(t.nreg + m0);   // (the same, as an address for the asynchronous copies)
+    uint32_t ranks[8];
     if (!METH) {
         const uint32_t P = ((((dg[0] & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dg[1] & 0x03030303u) * 0x40100401u) >> 24) << 16) |
                            ((((dg[2] & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dg[3] & 0x03030303u) * 0x40100401u) >> 24);
-        if (SINGLE) {
-            const float2 *tab = p.model;   // (ideal amplitudes: the raw level_mean, in double below)
-            const int sh0 = 32 - 2 * p.k;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t r = (P >> (sh0 - 2 * j)) & p.kmask;
-                if (nk_tile < TK && m0 + j >= nk_tile) r = 0;
-                mv[j] = __ldg(&tab[r]);
-            }
-        } else if (QUAD) {
-            // k <= 6: two 256-bit gathers, each the four k-mers of one (k+3)-mer = one whole sector
-            const int shq = 26 - 2 * p.k;             // 32 - 2(k+3)
-            const uint32_t qmask = (p.kmask << 6) | 63u;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t r = (P >> (shq - 8 * h)) & qmask;
-                if (nk_tile < TK && m0 + 4 * h >= nk_tile) r = 0;
-                const float4 *src = p.quad_model + 2 * (size_t)r;
-                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=f"(mv4[2 * h].x), "=f"(mv4[2 * h].y), "=f"(mv4[2 * h].z), "=f"(mv4[2 * h].w), "=f"(mv4[2 * h + 1].x),
-                               "=f"(mv4[2 * h + 1].y), "=f"(mv4[2 * h + 1].z), "=f"(mv4[2 * h + 1].w)
-                             : "l"(src));
-            }
-        } else {
+        if (NOISY && (t.nreg & 1) == 0) {
             const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
             const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint32_t r = (P >> (sh0 - 4 * ((j + rot4) & 3))) & pmask;
-                if (nk_tile < TK && m0 + 2 * ((j + rot4) & 3) >= nk_tile) r = 0;
-                mv4[j] = __ldg(&p.pair_model[r]);
+                const uint32_t r = (P >> (sh0 - 4 * j)) & pmask;
+#ifdef SQG_KO_GATHER
+                if (m0 + 2 * j < nk_tile) cp_async16(par_a + 16 * j, &p.pair_model[(td.nk & 0xFF) * 128 + j * 32 + lane]);   // coalesced (timing only)
+#else
+                if (m0 + 2 * j < nk_tile) cp_async16(par_a + 16 * j, &p.pair_model[r]);
+#endif
             }
+        } else {
+            const int sh0 = 32 - 2 * p.k;
+#pragma unroll
+            for (int j = 0; j < 8; j++) ranks[j] = (P >> (sh0 - 2 * j)) & p.kmask;
         }
     } else {
         // base-5 (CpG) ranks, src/seq.h:62-74, rolled: rank' = 5*rank - 5^k*(leading digit) + (new digit)
-        const float2 *tab = NOISY ? p.model_am : p.model;
         const uint32_t dw[4] = {dg[0], dg[1], dg[2], dg[3]};
         const int km1 = p.k - 1;
         uint32_t rank = 0;
@@ -501,87 +580,84 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
             const int bi = km1 + j;
             const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
             rank = rank * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);             // k digits: the k-mer at lane position j
-            mv[j] = __ldg(&tab[(m0 + j < nk_tile) ? rank : 0u]);
+            ranks[j] = rank;
             rank -= ((dw[j >> 2] >> (8 * (j & 3))) & 0xFFu) * p.kmask;        // drop its leading digit (kmask = 5^(k-1))
         }
     }
+    if (METH || !NOISY || (t.nreg & 1) != 0) {
+        // one gather per k-mer, by rank: CpG models, ideal amplitudes, and a window position the 16-byte copies cannot take
+        // (a second segment behind an odd number of k-mers)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (m0 + j < nk_tile) {
+                if (NOISY) cp_async8(par_a + 8 * j, &p.model_am[ranks[j]]);
+                else mv[j] = __ldg(&p.model[ranks[j]]);
+            }
+        }
+    }
+    if (NOISY) cp_async_commit();
 
     // (2) k-mer starts into the map.  Frame position of k-mer i of the tile = (frame position of the tile) + (prefix of
-    // the dwells before it, from K1): bit (pos & 31) of entry pos >> 5.  An entry's `base` is the par[] index of the k-mer
-    // that owns its first sample MINUS the number of starts... precisely: k-mer index = base + popcount(start bits at or
-    // before the sample); the first k-mer starting in an entry writes base = (its index - 1) there and into the empty
-    // entries between its predecessor's start and its own.
+    // the dwells before it, from K1): bit (pos & 31) of entry pos >> 5.  Then the entries' `base` words: the k-mer (index
+    // into par[]) of a sample is base + popcount(start bits at or before the sample), so base[e+1] = base[e] +
+    // popcount(bits[e]) - a warp scan over the window's entries, six per lane, starting from the entry that holds the
+    // tile's first sample (whose base is already valid) rounded down to a 16-byte boundary.
+#ifdef SQG_KO_MAP
+    if (false) {
+#else
     if (RAND_DWELL) {
+#endif
         const uint4 pq = *reinterpret_cast<const uint4 *>(smem + map_off + W_PL + lane * 16);
         const uint32_t mrel = t.f_end - t.fmap;      // the tile's first sample, relative to map entry 0
         const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
-        uint32_t e[8], pos[8];
+        if (nk_tile == TK) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            pos[j] = mrel + ((j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xFFFFu));
-            e[j] = pos[j] >> 5;
-        }
-        int32_t ep = (int32_t)__shfl_up_sync(0xffffffffu, e[7], 1);
-        if (lane == 0) ep = t.last_e;
-        const int32_t idx0 = t.nreg + m0;
-        int32_t my_last = -1;
+            for (int j = 0; j < 8; j++) {
+                const uint32_t pos = mrel + ((j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xFFFFu));
+                atomicOr(reinterpret_cast<uint32_t *>(smem + map_off + W_MAP + 8 * (pos >> 5)), __funnelshift_l(0u, 1u, pos));
+            }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (nk_tile == TK || m0 + j < nk_tile) {
-                const uint32_t ea = map_off + W_MAP + 8 * e[j];
-                atomicOr(reinterpret_cast<uint32_t *>(smem + ea), __funnelshift_l(0u, 1u, pos[j]));
-                if ((int32_t)e[j] != ep) {
-                    for (int32_t x = ep + 1; x <= (int32_t)e[j]; x++) *reinterpret_cast<int32_t *>(smem + map_off + W_MAP + 8 * x + 4) = idx0 + j - 1;
-                }
-                ep = (int32_t)e[j];
-                my_last = ep;
+            for (int j = 0; j < 8; j++) {
+                const uint32_t pos = mrel + ((j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xFFFFu));
+                if (m0 + j < nk_tile) atomicOr(reinterpret_cast<uint32_t *>(smem + map_off + W_MAP + 8 * (pos >> 5)), __funnelshift_l(0u, 1u, pos));
             }
         }
-        // the last k-mer's start entry (entries are monotone over the lanes), and the entries it owns after that
-        const int32_t e_last = __reduce_max_sync(0xffffffffu, my_last);
-        const int32_t e_end = (int32_t)((mrel + td.S - 1) >> 5);
-        for (int32_t x = e_last + 1 + lane; x <= e_end; x += 32) *reinterpret_cast<int32_t *>(smem + map_off + W_MAP + 8 * x + 4) = t.nreg + nk_tile - 1;
-        t.last_e = e_last;
+        __syncwarp();
+        const uint32_t e_al = (mrel >> 5) & ~1u;
+        const uint32_t e_mine = e_al + 6u * (uint32_t)lane;
+        const bool inw = e_mine + 6u <= (uint32_t)(MAP_ENT + 2);   // (MAP_ENT + 2 is a multiple of 2; partial sixes at the end are left alone:
+                                                                    //  the window check keeps the tile's samples below them)
+        uint4 w[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        uint4 *ep = reinterpret_cast<uint4 *>(smem + map_off + W_MAP + 8 * e_mine);
+        if (inw) { w[0] = ep[0]; w[1] = ep[1]; w[2] = ep[2]; }
+        const uint32_t c0 = __popc(w[0].x), c1 = __popc(w[0].z), c2 = __popc(w[1].x), c3 = __popc(w[1].z), c4 = __popc(w[2].x), c5 = __popc(w[2].z);
+        const uint32_t mine = c0 + c1 + c2 + c3 + c4 + c5;
+        uint32_t run = mine;
+#pragma unroll
+        for (int sh = 1; sh < 32; sh <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, run, sh);
+            if (lane >= sh) run += v;
+        }
+        const uint32_t b0 = __shfl_sync(0xffffffffu, w[0].y, 0) + run - mine;   // base of this lane's first entry
+        if (inw) {
+            ep[0] = make_uint4(w[0].x, b0, w[0].z, b0 + c0);
+            ep[1] = make_uint4(w[1].x, b0 + c0 + c1, w[1].z, b0 + c0 + c1 + c2);
+            ep[2] = make_uint4(w[2].x, b0 + c0 + c1 + c2 + c3, w[2].z, b0 + c0 + c1 + c2 + c3 + c4);
+        }
     }
 
-    // (3) the parameters of this lane's 8 k-mers
-    const float c_r = t.c_r;
-    const double off_d = t.offset;
-    const bool wide = p.wide != 0;
-    auto make_par = [&](float a, float m) -> float2 {
-        if (NOISY) {
-            // (a, m) = (A', M): B' + 32768 = M + c_r, one rounding (wide mode keeps Bq = (B' + 32768) - 32768 itself)
-            const float Bm = __fadd_rn(m, c_r);
-            return make_float2(a, wide ? __fsub_rn(Bm, SAMPLE_MAGIC) : Bm);
-        } else {
-            // (a, m) = (level_mean, level_stdv); src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated
-            const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)a, p.digitisation), p.range), off_d);
-            return make_float2(0.f, __uint_as_float(to_i16_bits(v)));
-        }
-    };
-    const uint32_t par_w = map_off + W_PAR + 8 * (uint32_t)(t.nreg + m0);
-    if (m0 < nk_tile) {
-        if (SINGLE) {
-            if (NOISY) {   // METH: table of (A', M)
+    // (3) the parameters of this lane's 8 k-mers.  Noisy modes: they are arriving by themselves.  Ideal amplitudes:
+    // src/gensig.c:266,270: (double)level_mean*digitisation/range - offset, truncated - the sample itself.
+    if (NOISY) {
+        cp_async_wait_all();
+    } else {
+        const double off_d = t.offset;
 #pragma unroll
-                for (int j = 0; j < 8; j++) *reinterpret_cast<float2 *>(smem + par_w + 8 * j) = make_par(mv[j].x, mv[j].y);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) *reinterpret_cast<float2 *>(smem + par_w + 8 * j) = make_par(mv[j].x, mv[j].y);
-            }
-        } else if ((t.nreg & 1) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float2 pa = make_par(mv4[j].x, mv4[j].y), pb = make_par(mv4[j].z, mv4[j].w);
-                const int piece = QUAD ? j : ((j + rot4) & 3);   // (the 256-bit gathers arrive in k-mer order)
-                *reinterpret_cast<float4 *>(smem + par_w + 16 * piece) = make_float4(pa.x, pa.y, pb.x, pb.y);
-            }
-        } else {   // odd window position (a second segment behind an odd number of k-mers): 8-byte stores
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int piece = QUAD ? j : ((j + rot4) & 3);
-                *reinterpret_cast<float2 *>(smem + par_w + 16 * piece) = make_par(mv4[j].x, mv4[j].y);
-                *reinterpret_cast<float2 *>(smem + par_w + 16 * piece + 8) = make_par(mv4[j].z, mv4[j].w);
+        for (int j = 0; j < 8; j++) {
+            if (m0 + j < nk_tile) {
+                const double v = __dsub_rn(__ddiv_rn(__dmul_rn((double)mv[j].x, p.digitisation), p.range), off_d);
+                *reinterpret_cast<float2 *>(smem + par_w + 8 * j) = make_float2(0.f, __uint_as_float(to_i16_bits(v)));
             }
         }
     }
@@ -594,37 +670,36 @@ template <bool RAND_DWELL>
 __device__ __forceinline__ void slide_window(const GenParams &p, int lane, unsigned char *smem, uint32_t map_off, Run &t) {
     const uint32_t gdone = (8 * t.cur_c - t.fmap) >> 8;   // whole groups emitted since the map's origin
     if (gdone == 0) return;
+#ifdef SQG_KO_SLIDE
+    if (t.f_end != 0x7FFFFFFFu) { t.nreg = 0; t.fmap += GROUP_S * gdone; return; }
+#endif
     const uint32_t fmap2 = t.fmap + GROUP_S * gdone;
     int32_t kt;       // first k-mer still needed (kept even: parameter stores are 16 bytes wide)
     int32_t n_ent = 0;
     const uint32_t e_sh = 8 * gdone;
     if (RAND_DWELL) {
-        if (t.f_end <= fmap2) {
-            kt = t.nreg;
-        } else {
-            const uint2 ent = *reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * e_sh);
-            kt = (int32_t)(ent.y + (ent.x & 1u));
-            n_ent = (int32_t)((t.f_end - 1 - t.fmap) >> 5) - (int32_t)e_sh + 1;
-        }
+        // (every entry of the window has a valid base after register_tile's scan, the one behind the last sample included)
+        const uint2 ent = *reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * e_sh);
+        kt = (int32_t)(ent.y + (ent.x & 1u));
+        n_ent = (int32_t)((t.f_end - t.fmap) >> 5) - (int32_t)e_sh + 1;   // <= 9: less than a group, and the entry of the next sample
     } else {
         const int32_t d = (int32_t)fmap2 - t.fix_f0;
         kt = d > 0 ? (int32_t)div_sps(p, (uint32_t)d) : 0;
-        kt = min(kt, t.nreg);
     }
-    kt &= ~1;
+    kt = max(min(kt, t.nreg), 0) & ~1;
     __syncwarp();
     if (kt > 0) {
         const int32_t n = t.nreg - kt;
-        for (int32_t i0 = 0; i0 < n; i0 += 128) {
-            float2 v[4];
+        for (int32_t i0 = 0; i0 < n; i0 += 64) {
+            float2 v[2];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 const int32_t i = i0 + lane + 32 * u;
                 if (i < n) v[u] = *reinterpret_cast<const float2 *>(smem + map_off + W_PAR + 8 * (kt + i));
             }
             __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 const int32_t i = i0 + lane + 32 * u;
                 if (i < n) *reinterpret_cast<float2 *>(smem + map_off + W_PAR + 8 * i) = v[u];
             }
@@ -636,12 +711,9 @@ __device__ __forceinline__ void slide_window(const GenParams &p, int lane, unsig
         uint2 ent = make_uint2(0u, 0u);
         if (lane < n_ent) ent = *reinterpret_cast<const uint2 *>(smem + map_off + W_MAP + 8 * (e_sh + lane));
         __syncwarp();
-        for (int32_t x = lane; x < MAP_ENT + 2; x += 32) {
-            uint2 w = make_uint2(0u, 0u);
-            if (x < n_ent) w = make_uint2(ent.x, ent.y - (uint32_t)kt);   // (n_ent <= 10: a group and the entry after it)
-            *reinterpret_cast<uint2 *>(smem + map_off + W_MAP + 8 * x) = w;
-        }
-        t.last_e = max(t.last_e - (int32_t)e_sh, -1);
+        for (int32_t x = lane; x < (MAP_ENT + 2) / 2; x += 32) *reinterpret_cast<uint4 *>(smem + map_off + W_MAP + 16 * x) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        if (lane < n_ent) *reinterpret_cast<uint2 *>(smem + map_off + W_MAP + 8 * lane) = make_uint2(ent.x, ent.y - (uint32_t)kt);
     } else {
         t.fix_f0 += kt * p.sps_fixed;
     }
@@ -652,10 +724,6 @@ __device__ __forceinline__ void slide_window(const GenParams &p, int lane, unsig
 
 // A tile with more samples than the window holds (T is chosen so that this takes a six-sigma run of long dwells): every
 // lane walks k-mers of its own and stores sample by sample.  Unconditionally correct, never fast.
-__device__ __forceinline__ uint32_t draw_word_dyn(const uint4 &w, uint32_t j) {
-    const uint32_t x = (j >> 1) == 0 ? w.x : (j >> 1) == 1 ? w.y : (j >> 1) == 2 ? w.z : w.w;
-    return (j & 1u) ? __byte_perm(x, x, 0x1032) : x;
-}
 template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
 __device__ __noinline__ void slow_tile(const GenParams &p, const unsigned char *smem, int lane, int tile, int64_t a_off, int64_t b_off,
                                        int32_t a_rem, int32_t nk, uint32_t B, uint32_t S, uint32_t L, int16_t *out, double offset,
@@ -694,8 +762,12 @@ __device__ __noinline__ void slow_tile(const GenParams &p, const unsigned char *
             uint32_t v = fixed_v;
             if (NOISY) {
                 const uint32_t Cq = q >> 3;
-                const uint4 r4 = philox4x32_rk(Cq, r_lo, r_hi, ST_AMP, p.rk);
-                const uint32_t off = z_offset(draw_word_dyn(r4, q & 7u), amp_class4(Cq, hmul));
+                uint32_t dw[8];
+                amp_draws(p, Cq, r_lo, r_hi, dw);
+                uint32_t word = dw[0];
+#pragma unroll
+                for (int e = 1; e < 8; e++) word = (q & 7u) == (uint32_t)e ? dw[e] : word;
+                const uint32_t off = z_offset(word, amp_class4(Cq, hmul));
                 float z = *reinterpret_cast<const float *>(smem + SM_Z + off);
                 if (z_is_tail(off)) z = z_tail(p.z2, off, q, key, ST_AMP_TAIL);
                 v = sample_exact(z, A, Bq);
@@ -784,53 +856,61 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
 
         // ---- does the tile fit behind what the window still holds?  (else the run is cut here: the group in progress is
         // finished by the exact path on both sides of the cut, exactly like a range boundary) ----
+        bool cut = false;
         if (active) {
             bool fits = t.nreg + td.nk <= p.par_cap;
-            if (RAND_DWELL) fits = fits && ((t.f_end - t.fmap + td.S + 31) >> 5) + 2 <= (uint32_t)MAP_ENT;
-            if (!fits || td.S > p.tile_s_cap) {
-                emit_ready<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, true, t.f_end);
-                active = false;
+            if (RAND_DWELL) fits = fits && ((t.f_end - t.fmap + td.S + 31) >> 5) + 8 <= (uint32_t)MAP_ENT;
+            cut = !fits || td.S > p.tile_s_cap;
+        }
+        const bool slow = td.S > p.tile_s_cap;
+        // pass 0 (only after a cut): the run ends with what is registered; pass 1: the tile itself
+        for (int pass = cut ? 0 : 1; pass < 2; pass++) {
+            bool lst = true;
+            uint32_t clip_hi = t.f_end;
+            if (pass == 1) {
+                if (!active) {
+                    // ---- a run begins: the read's constants, the frame, an empty window ----
+                    const ReadRec rr = *reinterpret_cast<const ReadRec *>(smem + rd_off);
+                    t.L = rr.L;
+                    t.offset = rr.offset;
+                    t.out = p.sig + rr.sigoff;
+                    t.c_r = __fsub_rn(SAMPLE_MAGIC, (float)t.offset);
+                    const uint64_t rg = (((uint64_t)r0_hi << 32) | r0_lo) + (uint64_t)(int64_t)read;
+                    t.r_lo = (uint32_t)rg; t.r_hi = (uint32_t)(rg >> 32);
+                    t.hmul = amp_hmul(t.r_lo);
+                    if (!slow) {
+                        // frame origin: the unit boundary of the emitted signal at or before the run's first sample
+                        const uint32_t delta = REV ? (UNIT_S - (t.L - B) % UNIT_S) % UNIT_S : B % UNIT_S;
+                        t.C0 = REV ? ((t.L - B + delta) >> 3) - 1u : (B - delta) >> 3;
+                        // a run that does not start its read starts where another warp's range (or a cut) ended: exactly there
+                        t.clip_lo = rfirst ? 0u : delta;
+                        t.f_end = delta;
+                        t.fmap = delta & ~(GROUP_S - 1);
+                        t.cur_c = delta >> 3;
+                        t.nreg = 0;
+                        t.fix_f0 = (int32_t)delta;
+                        if (RAND_DWELL)
+                            for (int32_t x = lane; x < MAP_ENT + 2; x += 32) *reinterpret_cast<uint2 *>(smem + map_off + W_MAP + 8 * x) = make_uint2(0u, 0xFFFFFFFFu);
+                        if (lane == 0) *reinterpret_cast<float2 *>(smem + map_off + W_PARG + 8) = make_float2(0.f, NOISY ? __fsub_rn(SAMPLE_MAGIC, t.c_r) : 0.f);
+                        active = true;
+                        __syncwarp();
+                    }
+                }
+                if (slow) {
+                    slow_tile<NOISY, RAND_DWELL, METH, REV>(p, smem, lane, tile, td.a_off, td.b_off, td.a_rem, td.nk, B, td.S, t.L, t.out, t.offset, t.r_lo, t.r_hi);
+                    prefetch_next();
+                    break;
+                }
+                register_tile<NOISY, RAND_DWELL, METH, REV, QUAD && !METH>(p, lane, smem, map_off, wbase, t, td);
+                prefetch_next();
+                t.f_end += td.S;
+                lst = last;
+                clip_hi = rlast ? 0xFFFFFFFFu : t.f_end;
             }
+            emit_ready<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, lane, lst, clip_hi);
+            if (lst) active = false;
+            else slide_window<RAND_DWELL>(p, lane, smem, map_off, t);
         }
-        if (!active) {
-            // ---- a run begins: the read's constants, the frame, an empty window ----
-            const int64_t sigoff = *reinterpret_cast<const int64_t *>(smem + rd_off);
-            t.L = *reinterpret_cast<const uint32_t *>(smem + rd_off + 8);
-            t.offset = *reinterpret_cast<const double *>(smem + rd_off + 16);
-            t.out = p.sig + sigoff;
-            t.c_r = __fsub_rn(SAMPLE_MAGIC, (float)t.offset);
-            const uint64_t rg = (((uint64_t)r0_hi << 32) | r0_lo) + (uint64_t)(int64_t)read;
-            t.r_lo = (uint32_t)rg; t.r_hi = (uint32_t)(rg >> 32);
-            t.hmul = amp_hmul(t.r_lo);
-        }
-        if (td.S > p.tile_s_cap) {
-            slow_tile<NOISY, RAND_DWELL, METH, REV>(p, smem, lane, tile, td.a_off, td.b_off, td.a_rem, td.nk, B, td.S, t.L, t.out, t.offset, t.r_lo, t.r_hi);
-            prefetch_next();
-            continue;
-        }
-        if (!active) {
-            const uint32_t delta = REV ? ((GROUP_S - ((t.L - B) & (GROUP_S - 1))) & (GROUP_S - 1)) : (B & (GROUP_S - 1));
-            t.C0 = REV ? ((t.L - B + delta) >> 3) - 1u : (B - delta) >> 3;
-            // a run that does not start its read starts where another warp's range (or a slow tile) ended: exactly there
-            t.clip_lo = (rfirst) ? 0u : delta;
-            t.f_end = delta;
-            t.fmap = 0;
-            t.cur_c = delta >> 3;
-            t.nreg = 0;
-            t.last_e = -1;
-            t.fix_f0 = (int32_t)delta;
-            if (RAND_DWELL)
-                for (int32_t x = lane; x < MAP_ENT + 2; x += 32) *reinterpret_cast<uint2 *>(smem + map_off + W_MAP + 8 * x) = make_uint2(0u, 0xFFFFFFFFu);
-            if (lane == 0) *reinterpret_cast<float2 *>(smem + map_off + W_PARG + 8) = make_float2(0.f, NOISY ? SAMPLE_MAGIC : 0.f);
-            active = true;
-            __syncwarp();
-        }
-        register_tile<NOISY, RAND_DWELL, METH, REV, QUAD && !METH>(p, lane, smem, map_off, t, td);
-        prefetch_next();
-        t.f_end += td.S;
-        emit_ready<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, last, rlast ? 0xFFFFFFFFu : t.f_end);
-        if (last) active = false;
-        else slide_window<RAND_DWELL>(p, lane, smem, map_off, t);
     }
 }
 

@@ -19,10 +19,10 @@ def sq():
 
 
 def run_pair(sq, oracle_lib, ztable, profile, flags, k, reads, seed=11, meth=False, amp_noise=1.0, first=0, want_ss=True,
-             model=None):
+             model=None, tuning=0):
     num_kmer = (5 if meth else 4) ** k
     model = H.random_model(num_kmer) if model is None else model
-    gen = sq.SignalGenerator(dict(profile), model, k, flags=flags, seed=seed, meth=meth, amp_noise=amp_noise)
+    gen = sq.SignalGenerator(dict(profile), model, k, flags=flags, seed=seed, meth=meth, amp_noise=amp_noise, tuning=tuning)
     got = gen.gen_batch(reads, first_read_index=first, want_ss=want_ss)
     gen.close()
     o = H.Oracle(oracle_lib, profile, flags, k, num_kmer, model, seed, H.RNG_PHILOX, meth=int(meth), amp_noise=amp_noise,
@@ -76,6 +76,19 @@ def test_edge_cases(sq, oracle_lib, ztable):
     prof, pflags = H.PRESETS["rna-r9-prom"]
     run_pair(sq, oracle_lib, ztable, prof, pflags, 5, [b"", b"AC", b"ACGTA", b"ACGTAC", b"G" * 3000], first=3)
     run_pair(sq, oracle_lib, ztable, prof, pflags | H.SQ_PREFIX, 5, [b"", b"AC", b"G" * 700], first=3)
+
+
+def test_window_fallback_paths(sq, oracle_lib, ztable):
+    """The signal kernel keeps a sliding window of k-mers per warp; a run of tiles is CUT when the next tile does not fit
+    behind what the window still holds, and a tile that could never fit is generated sample by sample (slow path).
+    Neither happens with sane profiles at default sizes, so the testing knob (sqg_config_t::reserved: low 16 bits =
+    samples per tile the fast path accepts, high bits = k-mers the window holds) shrinks the window until they do."""
+    reads = H.random_reads(10, 4000, seed=77) + [b"ACGT" * 2000, b"A" * 300]
+    for preset, k, xflags in (("dna-r10-prom", 9, 0), ("dna-r9-prom", 6, 0), ("rna-r9-prom", 5, 0), ("rna004-prom", 9, 0),
+                              ("rna-r9-prom", 5, H.SQ_PREFIX), ("dna-r10-prom", 9, H.SQ_IDEAL_AMP)):
+        prof, pflags = H.PRESETS[preset]
+        for tuning in ((262 << 16), (300 << 16) | 3000, 1500, (258 << 16) | 40000):
+            run_pair(sq, oracle_lib, ztable, prof, pflags | xflags, k, reads, first=5, tuning=tuning)
 
 
 def test_empty_batch(sq):
