@@ -856,6 +856,9 @@ int ctx_setup(sqg_ctx *ctx, const sqg_config_t *cfg) {
         while (T > 8 && (T * dm + 6.0 * ds * std::sqrt((double)T) > (double)TILE_S_CAP || T * mx >= 65000.0)) T -= 8;
         b.T = T;
         b.tile_s_cap = TILE_S_CAP;
+        // a chunk of 8 samples holds three k-mers only if one of them has a dwell <= 6: the warp-wide vote pays when that is rare
+        b.l2_vote = (mu - 6.0) / std::max(sg, 1e-9) > 1.3 ? 1 : 0;
+        if (const char *e = getenv("SQG_L2_VOTE")) b.l2_vote = atoi(e);   // (experiments)
     } else {
         // n / sps == umulhi(n, magic) needs n * sps < 2^32 for every window sample n < par_cap * sps
         const uint64_t sps = (uint64_t)b.sps_fixed;

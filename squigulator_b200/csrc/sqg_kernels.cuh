@@ -100,6 +100,7 @@ struct GenParams {
     int32_t wide;      // 1: the model/profile does not guarantee 16384 <= sample + 32768 < 131072 -> exact path for every sample
     uint32_t pow5k;    // base 5: 5^k
     int32_t par_cap;      // k-mers the signal kernel's window may hold (<= PAR_N; fixed-dwell modes: bounded by the exact division)
+    int32_t l2_vote;      // signal kernel: skip a chunk's third k-mer level when no lane of the warp has one (pays with long dwells)
     uint32_t tile_s_cap;  // a tile with more samples than this goes through the signal kernel's slow path (statistically unreachable)
     // profile (src/sq.h:47-58) and options
     double digitisation, range, scale;  // scale = digitisation/range

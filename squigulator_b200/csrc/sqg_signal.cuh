@@ -48,10 +48,10 @@ constexpr int DIG_BYTES = TK + 32;         // digits of the tile's base window; 
 // per-warp buffer
 constexpr uint32_t W_MAP = 0;                               // MAP_ENT (+2 that the one-ahead loads may touch) x {bits, base}
 constexpr uint32_t W_PARG = W_MAP + (MAP_ENT + 2) * 8;      // guard entry par[-1] (the padding chunk of a reversed read)
-constexpr uint32_t W_PAR = W_PARG + 16;                     // par[0 .. PAR_N) + 4 rows the sample loop may load past the end
+constexpr uint32_t W_PAR = W_PARG + 16;                     // par[0 .. PAR_N) + 4 rows the sample loop may load past the end (k0 + 3 <= last + 3)
 constexpr uint32_t W_RAW = W_PAR + (PAR_N + 4) * 8;         // prefetched base window (ASCII), 16-byte granules
-constexpr uint32_t W_DIG = W_RAW + DIG_BYTES;               // base digits (table path only)
-constexpr uint32_t W_PL = W_DIG + DIG_BYTES;                // prefetched prefix row of the tile: TK x uint16
+constexpr uint32_t W_DIG = W_RAW;                           // base digits (table path only): converted in place
+constexpr uint32_t W_PL = W_RAW + DIG_BYTES;                // prefetched prefix row of the tile: TK x uint16
 constexpr uint32_t W_DESC = W_PL + TK * 2;                  // two TileDesc slots
 constexpr uint32_t W_RD = W_DESC + 2 * 48;                  // two slots of {arena offset (8), samples in the read (4), pad, ADC offset (8), pad}
 constexpr uint32_t WARP_BYTES = W_RD + 2 * 32;
@@ -253,16 +253,15 @@ __device__ __noinline__ void exact_chunk(const GenParams &p, const unsigned char
 // (flagged sample, 4+ k-mers).
 template <bool NOISY, bool REV>
 __device__ __forceinline__ uint32_t fast_chunk(uint32_t k0, uint32_t m1, uint32_t par_base, const uint32_t (&dw)[8], uint32_t class4, float c_r,
-                                               uint4 &pk) {
+                                               bool l2_vote, bool converged, uint4 &pk) {
     const uint32_t par0 = k0 * 8 + par_base;
-    float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0), q2 = lds_f2<16>(par0);
+    float2 q0 = lds_f2<0>(par0), q1 = lds_f2<8>(par0);
     if (NOISY) {   // par[] holds (A', M): B' + 32768 = M + c_r, one rounding
-        q0.y = __fadd_rn(q0.y, c_r); q1.y = __fadd_rn(q1.y, c_r); q2.y = __fadd_rn(q2.y, c_r);
+        q0.y = __fadd_rn(q0.y, c_r); q1.y = __fadd_rn(q1.y, c_r);
     }
     const uint32_t t1 = m1 - 1u;        // bit j clear  <=>  slot j lies at or after the 1st boundary
     const uint32_t m2 = m1 & t1;        // boundaries after the first
-    const uint32_t t2 = m2 - 1u;        // bit j clear  <=>  slot j lies at or after the 2nd boundary
-    const uint32_t m3 = m2 & t2;        // non-zero: a 3rd boundary -> exact path
+    uint32_t m3 = 0;                    // non-zero after the levels: more boundaries than they cover -> exact path
     uint32_t bad;
     if (NOISY) {
         float zz[8], v[8];
@@ -276,10 +275,30 @@ __device__ __forceinline__ uint32_t fast_chunk(uint32_t k0, uint32_t m1, uint32_
             const int j = REV ? 7 - e : e;
             if (j >= 1 && !(t1 & (1u << j))) v[e] = fma_rz(zz[e], q1.x, q1.y);
         }
+        // a third k-mer in the chunk: with long dwells few chunks have one, and then (l2_vote) the level is skipped
+        // whenever no lane of the warp needs it; a fourth one is rare with every profile, but not rare enough (dwell 9 +- 4:
+        // one chunk in 300) to send its chunk through the exact path: its level runs when some lane of the warp has one
+        if (!l2_vote || __any_sync(0xffffffffu, m2 != 0)) {
+            float2 q2 = lds_f2<16>(par0);
+            q2.y = __fadd_rn(q2.y, c_r);
+            const uint32_t t2 = m2 - 1u;        // bit j clear  <=>  slot j lies at or after the 2nd boundary
+            m3 = m2 & t2;
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int j = REV ? 7 - e : e;
-            if (j >= 2 && !(t2 & (1u << j))) v[e] = fma_rz(zz[e], q2.x, q2.y);
+            for (int e = 0; e < 8; e++) {
+                const int j = REV ? 7 - e : e;
+                if (j >= 2 && !(t2 & (1u << j))) v[e] = fma_rz(zz[e], q2.x, q2.y);
+            }
+            if (converged && __any_sync(0xffffffffu, m3 != 0)) {
+                float2 q3 = lds_f2<24>(par0);
+                q3.y = __fadd_rn(q3.y, c_r);
+                const uint32_t t3 = m3 - 1u;    // bit j clear  <=>  slot j lies at or after the 3rd boundary
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int j = REV ? 7 - e : e;
+                    if (j >= 3 && !(t3 & (1u << j))) v[e] = fma_rz(zz[e], q3.x, q3.y);
+                }
+                m3 &= t3;                        // non-zero: a 4th boundary -> exact path
+            }
         }
         uint32_t u[8];
 #pragma unroll
@@ -290,6 +309,9 @@ __device__ __forceinline__ uint32_t fast_chunk(uint32_t k0, uint32_t m1, uint32_
         bad = ((pk.x | pk.y | pk.z | pk.w) & 0x80008000u) | m3;
     } else {
         uint32_t v[8];
+        const float2 q2 = lds_f2<16>(par0);
+        const uint32_t t2 = m2 - 1u;
+        m3 = m2 & t2;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = REV ? 7 - e : e;
@@ -324,7 +346,7 @@ __device__ __forceinline__ uint32_t group_chunk(const GenParams &p, const unsign
     // warp-uniform values so that the hash stays off the vector pipes
     const uint32_t Gq = REV ? (t.C0 >> 5) - g : (t.C0 >> 5) + g;
     const uint32_t class4 = lc.lane4 ^ (amp_class_hash(Gq, t.hmul) << 2);
-    return fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, pk);
+    return fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, false, false, pk);
 }
 
 // One group of 32 chunks by itself (where a run begins or ends): only frame chunks [c_lo, c_hi) are emitted, and those
@@ -348,33 +370,41 @@ __device__ __forceinline__ void emit_group_single(const GenParams &p, const unsi
 }
 
 // One whole unit: frame groups 3 uf .. 3 uf + 2.  Three independent chunks per lane from two Philox blocks, one check for
-// the rare redo behind them.
+// the rare redo behind them.  ent_addr / dst / blk / H walk from unit to unit in the caller: the lane's map entry of the
+// unit's first group, where its first chunk goes, its first Philox block, the class hash's argument of the first group.
 template <bool NOISY, bool RAND_DWELL, bool REV>
 __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
-                                               uint32_t uf, int lane) {
+                                               uint32_t uf, uint32_t ent_addr, int16_t *dst, uint32_t blk, uint32_t H) {
     uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
     if (NOISY) {
-        // emitted unit (warp-uniform: frame units are aligned with those of the emitted signal)
-        const uint32_t u = REV ? (t.C0 / UNIT_C) - uf : (t.C0 / UNIT_C) + uf;
-        const uint32_t blk = 64u * u + 2u * (uint32_t)lane;
         A = philox4x32_rk(blk, t.r_lo, t.r_hi, ST_AMP, p.rk);
         B = philox4x32_rk(blk + 1, t.r_lo, t.r_hi, ST_AMP, p.rk);
     }
-    uint32_t Cq[3], bad[3], dw[8];
+    uint32_t bad[3];
     uint4 pk[3];
-    // frame order = emitted order (reversed reads: the unit's chunks come last group first)
-    amp_fields<REV ? 2 : 0>(A, B, dw);
-    bad[0] = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, 3 * uf, dw, Cq[0], pk[0]);
-    amp_fields<1>(A, B, dw);
-    bad[1] = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, 3 * uf + 1, dw, Cq[1], pk[1]);
-    amp_fields<REV ? 0 : 2>(A, B, dw);
-    bad[2] = group_chunk<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, 3 * uf + 2, dw, Cq[2], pk[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        uint32_t k0, m1, dw[8];
+        if (RAND_DWELL) {
+            const uint2 ent = i == 0 ? lds_u2<W_MAP>(ent_addr) : i == 1 ? lds_u2<W_MAP + 64>(ent_addr) : lds_u2<W_MAP + 128>(ent_addr);
+            entry_kmers(ent, lc.ent_sh, k0, m1);
+        } else {
+            chunk_kmers<false>(p, smem, map_off, t.fmap, t.fix_f0, 32 * (3 * uf + i) + lc.lw, k0, m1);
+        }
+        // frame order = emitted order (reversed reads: the unit's chunks come last group first)
+        if (i == 0) amp_fields<REV ? 2 : 0>(A, B, dw);
+        else if (i == 1) amp_fields<1>(A, B, dw);
+        else amp_fields<REV ? 0 : 2>(A, B, dw);
+        const uint32_t Hi = REV ? H - (uint32_t)i * 0x9E3779B1u : H + (uint32_t)i * 0x9E3779B1u;   // (warp-uniform)
+        const uint32_t class4 = lc.lane4 ^ ((Hi >> 27) << 2);
+        bad[i] = fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, p.l2_vote != 0, true, pk[i]);
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
 #ifdef SQG_KO_STORE
         if (pk[i].x == 0x12345678u && pk[i].y == 0x9abcdef0u)
 #endif
-        st_cs_v4(t.out + (size_t)Cq[i] * 8, pk[i]);
+        st_cs_v4(REV ? dst - 256 * i : dst + 256 * i, pk[i]);
     }
     if (__builtin_expect((bad[0] | bad[1] | bad[2]) != 0, 0)) {
 #pragma unroll
@@ -399,7 +429,21 @@ __device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned ch
             uint32_t uf = t.cur_c / UNIT_C;
             const uint32_t u_end = min(hi_c, clip_hi >> 3) / UNIT_C;   // whole units: [uf, u_end)
             if (uf < u_end) {
-                for (; uf < u_end; uf++) emit_unit_fast<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, uf, lane);
+                // the lane's walk over the units: map entry, output chunk, Philox block, class hash of the first group
+                const uint32_t c0 = t.cur_c + lc.lw;
+                const uint32_t Cq0 = REV ? t.C0 - c0 : t.C0 + c0;
+                uint32_t ent_addr = map_off + 8 * ((8 * t.cur_c - t.fmap) >> 5) + lc.ent_lane;
+                int16_t *dst = t.out + (size_t)Cq0 * 8;
+                const uint32_t u0 = REV ? (t.C0 / UNIT_C) - uf : (t.C0 / UNIT_C) + uf;   // emitted unit (frame units are aligned with them)
+                uint32_t blk = 64u * u0 + 2u * (uint32_t)lane;
+                uint32_t H = (REV ? 3 * u0 + 2 : 3 * u0) * 0x9E3779B1u + t.hmul;
+                for (; uf < u_end; uf++) {
+                    emit_unit_fast<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, uf, ent_addr, dst, blk, H);
+                    ent_addr += 3 * 64;
+                    dst = REV ? dst - 768 : dst + 768;
+                    blk = REV ? blk - 64 : blk + 64;
+                    H = REV ? H - 3u * 0x9E3779B1u : H + 3u * 0x9E3779B1u;
+                }
                 t.cur_c = UNIT_C * u_end;
                 continue;
             }
@@ -513,14 +557,13 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
         if (!tile_is_junction(p, td.a_rem, nk_tile)) {
             const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
             const uint32_t raw_off = map_off + W_RAW + shift + lane;
-#pragma unroll 1
-            for (int u = 0; u < WIN_LOADS; u++) {
-                const int i = lane + 32 * u;
-                if (i < nb) {
-                    const uint32_t c = smem[SM_CODE + smem[raw_off + 32 * u]];
-                    smem[dig_off + i] = (unsigned char)(METH ? (c >> 4) : (c & 3u));
-                }
-            }
+            uint32_t cc[WIN_LOADS];
+#pragma unroll
+            for (int u = 0; u < WIN_LOADS; u++) cc[u] = (lane + 32 * u < nb) ? smem[SM_CODE + smem[raw_off + 32 * u]] : 0u;
+            __syncwarp();   // (the digits replace the raw bytes in place)
+#pragma unroll
+            for (int u = 0; u < WIN_LOADS; u++)
+                if (lane + 32 * u < nb) smem[dig_off + lane + 32 * u] = (unsigned char)(METH ? (cc[u] >> 4) : (cc[u] & 3u));
         } else {
 #pragma unroll 1
             for (int i = lane; i < nb; i += 32) {
@@ -553,6 +596,8 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
         if (NOISY && (t.nreg & 1) == 0) {
             const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
             const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
+            // (the 16-byte shared-memory writes of these copies collide in the banks - lane stride 64 bytes - but visiting the
+            // pairs in a rotated order to avoid that costs more in instructions than the replays do: measured)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t r = (P >> (sh0 - 4 * j)) & pmask;
@@ -587,12 +632,14 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
     if (METH || !NOISY || (t.nreg & 1) != 0) {
         // one gather per k-mer, by rank: CpG models, ideal amplitudes, and a window position the 16-byte copies cannot take
         // (a second segment behind an odd number of k-mers)
+        if (NOISY) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (m0 + j < nk_tile) {
-                if (NOISY) cp_async8(par_a + 8 * j, &p.model_am[ranks[j]]);
-                else mv[j] = __ldg(&p.model[ranks[j]]);
-            }
+            for (int j = 0; j < 8; j++)
+                if (m0 + j < nk_tile) cp_async8(par_a + 8 * j, &p.model_am[ranks[j]]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (m0 + j < nk_tile) mv[j] = __ldg(&p.model[ranks[j]]);
         }
     }
     if (NOISY) cp_async_commit();
