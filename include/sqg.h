@@ -79,7 +79,8 @@ typedef struct {
     int32_t rng_mode;      /* SQG_RNG_* */
     int32_t device;        /* CUDA device ordinal */
     int32_t n_slots;       /* batches in flight for sqg_submit (0 = default 3) */
-    int32_t reserved;
+    int32_t reserved;      /* 0.  (Testing knob, > 0: shrinks the signal kernel's window so that small inputs reach its
+                              cut-run and slow-tile paths - low 16 bits: samples per tile, high bits: k-mers.) */
 } sqg_config_t;
 
 typedef struct sqg_ctx sqg_ctx_t;
@@ -140,7 +141,10 @@ int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int6
 /* ---- asynchronous dispatcher: CUDA-stream slots instead of src/thread.c's pthread pool ----
  * sqg_submit returns as soon as the batch is queued on a free slot (it blocks only while all
  * n_slots are in flight); the inputs must stay valid until sqg_wait returns.  One submitter thread;
- * any thread may wait.  Results stay valid until sqg_release. */
+ * any thread may wait.  Results stay valid until sqg_release.  A ticket holds its slot until sqg_release - also
+ * when sqg_wait returned an error (sqg_last_error then carries that job's own message).
+ * SQG_RNG_LEGACY consumes the reference's streams in submission order: one slot, and sqg_gen_batch refuses to run
+ * while a submitted batch is in flight. */
 typedef int64_t sqg_ticket_t;
 int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
                int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket);

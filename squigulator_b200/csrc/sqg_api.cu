@@ -24,6 +24,7 @@
 
 #include "../../include/sqg.h"
 #include <cuda/functional>
+#include <nvtx3/nvToolsExt.h>
 
 #include "sqg_kernels.cuh"
 #include "sqg_signal.cuh"
@@ -39,6 +40,15 @@ namespace {
 using namespace sqg;
 
 thread_local std::string g_init_error;
+// where CU()/fail() put their message on this thread: a slot worker points it at its job, so that two batches failing at
+// once never write the same std::string and sqg_wait reports the message of ITS job
+thread_local std::string *tl_err_sink = nullptr;
+
+// NVTX range for the host-side stages of a batch (visible in nsys / ncu timelines)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // constant sequences of --prefix (src/genread.c:37-39, :88, :113) and of the short-read rule
 // (src/gensig.c:242-245), kept in front of every uploaded base buffer
@@ -186,6 +196,7 @@ struct Job {
     int status = 1;  // 1 = running, <=0 = done with that code
     const sqg_coord_t *coords = nullptr;  // coordinate batch (bases/base_off unused)
     int64_t meth_draw_base = 0;
+    std::string err;  // message of this job's failure (sqg_wait copies it to the context)
 };
 
 }  // namespace
@@ -203,7 +214,6 @@ struct sqg_ctx {
     DevBuf<float2> d_model;
     DevBuf<float2> d_model_am;    // (A', M) by rank (model_am_kernel)
     DevBuf<float4> d_pair_model;  // by (k+1)-mer: the parameters of both of its k-mers (base-4 models)
-    DevBuf<float4> d_quad_model;  // k <= 6: by (k+3)-mer, the parameters of its four k-mers (32-byte entries)
     DevBuf<unsigned char> d_z;  // Z32 ++ Z2
     // device-resident genome (sqg_genome_load)
     DevBuf<uint8_t> d_genome, d_gmeth, d_has_meth;
@@ -233,19 +243,25 @@ struct sqg_ctx {
 
 namespace {
 
+void set_error(sqg_ctx *ctx, const char *msg) {
+    if (tl_err_sink) *tl_err_sink = msg;
+    else if (ctx) ctx->err = msg;
+    else g_init_error = msg;
+}
+
 #define CU(call)                                                                                     \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \
         if (e__ != cudaSuccess) {                                                                    \
             char b__[512];                                                                           \
             snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-            ctx->err = b__;                                                                          \
+            set_error(ctx, b__);                                                                     \
             return e__ == cudaErrorMemoryAllocation ? SQG_ERR_NOMEM : SQG_ERR_CUDA;                  \
         }                                                                                            \
     } while (0)
 
 int fail(sqg_ctx *ctx, int code, const char *msg) {
-    if (ctx) ctx->err = msg; else g_init_error = msg;
+    set_error(ctx, msg);
     return code;
 }
 
@@ -254,7 +270,7 @@ typedef void (*k4_fn)(const GenParams);
 template <int I>
 struct K4Table {
     static void fill(k4_fn *t) {
-        t[I] = (k4_fn)signal_kernel<(I >> 4) & 1, (I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
+        t[I] = (k4_fn)signal_kernel<(I >> 3) & 1, (I >> 2) & 1, (I >> 1) & 1, I & 1>;
         K4Table<I - 1>::fill(t);
     }
 };
@@ -263,15 +279,12 @@ struct K4Table<-1> {
     static void fill(k4_fn *) {}
 };
 
-// the instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV, QUAD> (QUAD: (k+3)-mer model gathers, k <= 6)
-k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev, bool quad) {
-    static k4_fn tab[32];
-    static bool init = false;
-    if (!init) {
-        K4Table<31>::fill(tab);
-        init = true;
-    }
-    return tab[(noisy << 4) | (rnd << 3) | (meth << 2) | (rev << 1) | (int)(quad && !meth)];
+// the instantiations of the signal kernel: <NOISY, RAND_DWELL, METH, REV>
+k4_fn pick_k4(bool noisy, bool rnd, bool meth, bool rev) {
+    static k4_fn tab[16];
+    static std::once_flag once;
+    std::call_once(once, [] { K4Table<15>::fill(tab); });
+    return tab[(noisy << 3) | (rnd << 2) | (meth << 1) | (int)rev];
 }
 
 int slot_init(sqg_ctx *ctx, Slot &s) {
@@ -329,7 +342,8 @@ int slot_prepare(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
     const int stall_rna_len = (int)strlen(STALL_RNA);
     for (int64_t r = 0; r < n_reads; r++) {
         const int64_t len64 = base_off[r + 1] - base_off[r];
-        if (len64 < 0 || len64 > 0x7FFFFFF0) return fail(ctx, SQG_ERR_ARG, "read length out of range (int32, as in the reference)");
+        if (len64 < 0 || len64 > 0x7FFFFFF0 - 512)   // (- 512: prefix/suffix sequences are added to it in int32)
+            return fail(ctx, SQG_ERR_ARG, "read length out of range (int32, as in the reference)");
         const int len = (int)len64;
         const int64_t uoff = CONST_REGION + (base_off[r] - user0);
         ReadDesc &rd = s.h_reads.p[r];
@@ -614,7 +628,7 @@ int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent
     if (ctx->legacy) return slot_generate_legacy(ctx, s);
     const GenParams p = slot_params(ctx, s);
     const int grid = (int)std::min<int64_t>((s.n_tiles + K4_WARPS - 1) / K4_WARPS, (int64_t)ctx->num_sms * ctx->k4_grid_per_sm);
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->base.quad_model != nullptr);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
     if (before) CU(cudaEventRecord(before, s.stream));
     void *args[] = {(void *)&p};
     CU(cudaLaunchKernel((const void *)fn, dim3(grid), dim3(K4_THREADS), args, SM_TOTAL, s.stream));
@@ -725,7 +739,7 @@ int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     CU(s.h_len64.ensure(n + 1));
     CU(s.h_offset.ensure(n + 1));
     CU(s.h_median.ensure(n + 1));
-    CU(s.h_sig.ensure((size_t)std::max<int64_t>(s.arena_need, 64)));
+    CU(s.h_sig.ensure(svb ? 64 : (size_t)std::max<int64_t>(s.arena_need, 64)));   // (svb-zd: the raw signal stays in HBM)
     if (n) {
         if (!svb) CU(cudaMemcpyAsync(s.h_sig.p, s.d_sig.p, (size_t)s.arena_need * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_siglen.p, s.d_siglen.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
@@ -754,12 +768,25 @@ int slot_run_all(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
                  int64_t first_read, uint32_t want, sqg_result_t *res, const sqg_coord_t *coords = nullptr,
                  int64_t meth_draw_base = 0) {
     int rc;
-    if ((rc = slot_prepare(ctx, s, n_reads, bases, base_off, first_read, want, coords, meth_draw_base)) != SQG_OK) return rc;
-    if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
-    if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
-    if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
-    if ((want & SQG_WANT_SVB) && (rc = slot_compress(ctx, s)) != SQG_OK) return rc;
-    if ((want & SQG_WANT_SS_TEXT) && (rc = slot_sstext(ctx, s)) != SQG_OK) return rc;
+    {
+        NvtxRange r("sqg:prepare (segments, H2D)");
+        if ((rc = slot_prepare(ctx, s, n_reads, bases, base_off, first_read, want, coords, meth_draw_base)) != SQG_OK) return rc;
+    }
+    {
+        NvtxRange r("sqg:plan (tiles, dwells, offsets)");
+        if ((rc = slot_plan(ctx, s)) != SQG_OK) return rc;
+        if ((rc = slot_size_arena(ctx, s)) != SQG_OK) return rc;
+    }
+    {
+        NvtxRange r("sqg:generate (signal kernel)");
+        if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
+    }
+    if (want & (SQG_WANT_SVB | SQG_WANT_SS_TEXT)) {
+        NvtxRange r("sqg:compress (svb-zd, ss text)");
+        if ((want & SQG_WANT_SVB) && (rc = slot_compress(ctx, s)) != SQG_OK) return rc;
+        if ((want & SQG_WANT_SS_TEXT) && (rc = slot_sstext(ctx, s)) != SQG_OK) return rc;
+    }
+    NvtxRange r("sqg:fetch (D2H)");
     return slot_fetch(ctx, s, res);
 }
 
@@ -774,9 +801,10 @@ void worker_main(sqg_ctx *ctx, int slot_idx) {
             job = ctx->queues[slot_idx].front();
             ctx->queues[slot_idx].pop_front();
         }
-        // NB: ctx->err is shared; jobs report through their status code
+        tl_err_sink = &job->err;   // (this thread's CU()/fail() messages belong to the job)
         int rc = slot_run_all(ctx, ctx->slots[slot_idx], job->n_reads, job->bases, job->base_off, job->first_read,
                               job->want, nullptr, job->coords, job->meth_draw_base);
+        tl_err_sink = nullptr;
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
             job->status = rc;
@@ -922,14 +950,6 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
         ctx->base.pair_model = ctx->d_pair_model.p;
-        if (ctx->cfg.kmer_size <= 6 && ctx->cfg.kmer_size >= 1) {
-            const uint64_t n_quad = 64ull * n;   // 4^(k+3)
-            CU(ctx->d_quad_model.ensure((size_t)(2 * n_quad)));
-            quad_model_kernel<<<(unsigned)((n_quad + 255) / 256), 256>>>(ctx->d_model_am.p, ctx->d_quad_model.p, (uint32_t)n_quad, ctx->base.kmask);
-            CU(cudaGetLastError());
-            CU(cudaDeviceSynchronize());
-            ctx->base.quad_model = ctx->d_quad_model.p;
-        }
     }
     CU(cudaDeviceSynchronize());
     ctx->base.z32 = reinterpret_cast<const float *>(ctx->d_z.p);
@@ -960,7 +980,7 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     }
 
     CU(cudaFuncSetAttribute((const void *)dwell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
-    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev, ctx->base.quad_model != nullptr);
+    k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
     if (SM_TOTAL > prop.sharedMemPerBlockOptin) return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
     {
         // the sample loop addresses shared memory absolutely: dynamic array = reserved kilobyte + no static shared memory
@@ -1007,7 +1027,13 @@ int ensure_dispatcher(sqg_ctx *ctx) {
     ctx->slot_busy.assign(n, 0);
     for (int i = 0; i < n; i++) {
         int rc = slot_init(ctx, ctx->slots[i]);
-        if (rc != SQG_OK) return rc;
+        if (rc != SQG_OK) {   // no half-built dispatcher: the next sqg_submit starts over
+            for (auto &s : ctx->slots) s.release();
+            ctx->slots.clear();
+            ctx->queues.clear();
+            ctx->slot_busy.clear();
+            return rc;
+        }
     }
     for (int i = 0; i < n; i++) ctx->workers.emplace_back(worker_main, ctx, i);
     return SQG_OK;
@@ -1045,7 +1071,6 @@ void sqg_destroy(sqg_ctx_t *ctx) {
     ctx->d_model.release();
     ctx->d_model_am.release();
     ctx->d_pair_model.release();
-    ctx->d_quad_model.release();
     ctx->d_z.release();
     ctx->d_cnt_kmer.release();
     ctx->d_genome.release(); ctx->d_gmeth.release(); ctx->d_has_meth.release(); ctx->d_contig_off.release();
@@ -1066,6 +1091,11 @@ int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int6
                   int64_t first_read_index, uint32_t want, sqg_result_t *res) {
     if (!ctx || !res) return SQG_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
+    if (ctx->legacy) {   // the reference's streams are consumed in call order: no batch of the dispatcher may be in flight
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (int b : ctx->slot_busy)
+            if (b) return fail(ctx, SQG_ERR_STATE, "SQG_RNG_LEGACY: sqg_gen_batch while a submitted batch is in flight");
+    }
     return slot_run_all(ctx, ctx->sync_slot, n_reads, bases, base_off, first_read_index, want, res);
 }
 
@@ -1156,7 +1186,10 @@ int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res) {
     if (it == ctx->jobs.end()) return fail(ctx, SQG_ERR_STATE, "unknown ticket");
     Job *job = it->second;
     ctx->cv_done.wait(lk, [&] { return job->status <= 0; });
-    if (job->status != SQG_OK) return job->status;
+    if (job->status != SQG_OK) {
+        ctx->err = job->err;   // (under ctx->mu: sqg_last_error on the waiting thread sees this job's message)
+        return job->status;
+    }
     if (res) fill_result(ctx->slots[job->slot], res);
     return SQG_OK;
 }

@@ -74,7 +74,6 @@ struct GenParams {
     const float2 *model;     // (level_mean, level_stdv) by rank
     const float2 *model_am;  // (A', M) by rank: A' = (level_stdv*amp_noise)*scale, M = level_mean*scale, each rounded once (binary32)
     const float4 *pair_model;  // by (k+1)-mer rank: (A', M) of its two k-mers (first k bases, last k bases); base-4 models only
-    const float4 *quad_model;  // k <= 6: by (k+3)-mer rank, 32-byte entries: (A', M) of its four k-mers (else NULL)
     const float *z32;     // Z32[32768]
     const float *z2;      // Z2[8192]
     // plan (written by K0-K3, read by K4)
@@ -154,16 +153,6 @@ __global__ void __launch_bounds__(256) pair_model_kernel(const float2 *__restric
     pair[i] = make_float4(a.x, a.y, b.x, b.y);
 }
 
-// k <= 6: the same idea one step further - a (k+3)-mer spans four consecutive k-mers, 4 x 8 bytes = exactly one 32-byte
-// sector, fetched with one 256-bit load (LDG.E.256); 4^(k+3) x 32 B = 8 MB for 6-mers.
-__global__ void __launch_bounds__(256) quad_model_kernel(const float2 *__restrict__ am, float4 *__restrict__ quad, uint32_t n_quad, uint32_t kmask) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_quad) return;
-    const float2 a = am[(i >> 6) & kmask], b = am[(i >> 4) & kmask], c = am[(i >> 2) & kmask], d = am[i & kmask];
-    quad[2 * (size_t)i] = make_float4(a.x, a.y, b.x, b.y);
-    quad[2 * (size_t)i + 1] = make_float4(c.x, c.y, d.x, d.y);
-}
-
 // ------------------------------------------------------------------------------------------------
 // K0: tile descriptors (one warp per segment, one lane per tile)
 __global__ void __launch_bounds__(256) tile_desc_kernel(const __grid_constant__ GenParams p) {
@@ -215,6 +204,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) dwell_kernel(const __grid_const
     }
     __syncthreads();
     mbar_wait(bar, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {   // tail cells (NaN in the table file): +-infinity in this kernel's copy, see the dwell loop
+        reinterpret_cast<float *>(smem1)[Z_TAIL_IDX] = __int_as_float(0x7F800000);
+        reinterpret_cast<float *>(smem1)[Z_TAIL_IDX | 0x4000u] = __int_as_float(0xFF800000);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nw = K1_THREADS / 32;
     const int tile0 = blockIdx.x * nw + (threadIdx.x >> 5), tstride = gridDim.x * nw;
@@ -241,18 +236,38 @@ __global__ void __launch_bounds__(K1_THREADS, 1) dwell_kernel(const __grid_const
         if (lane * 8 < nk_tile) {
             const uint32_t blk = (kidx0 >> 3) + lane;
             const uint4 w = philox4x32_rk(blk, key.r_lo, key.r_hi, ST_DWELL, p.rk);
-            const int64_t ss0 = ss_pos + lane * 8;
+            const uint32_t class4 = (blk & 31u) << 2;
+            // The shared copy of the table holds +-infinity in the two tail cells (patched in the prologue): their dwell
+            // comes out of the conversion as INT_MAX / INT_MIN, so ONE test over the lane's eight dwells finds the draws
+            // that need the tail refinement.  A dwell below 1 is folded: d -> 1 - d, i.e. max(d, 1 - d).
+            uint32_t all = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t off = z_offset(draw_word(w, j), (blk & 31u) << 2);
-                float z = *reinterpret_cast<const float *>(smem1 + off);
-                if (__builtin_expect(z_is_tail(off), 0)) z = z_tail(p.z2, off, blk * 8 + j, key, ST_DWELL_TAIL);
-                if (lane * 8 + j < nk_tile) {
-                    d[j] = (uint32_t)dwell_from_z(z, p.dwell_mean, p.dwell_std);
-                    if (p.want_ss) p.ss[ss0 + j] = (int32_t)d[j];
-                }
-                sum += d[j];
+                const uint32_t off = z_offset(draw_word(w, j), class4);
+                const int dd = __float2int_rn(fmaf(*reinterpret_cast<const float *>(smem1 + off), p.dwell_std, p.dwell_mean));
+                d[j] = (uint32_t)max(dd, 1 - dd);
+                all |= d[j];
             }
+            if (__builtin_expect(all >= 0x10000u, 0)) {   // (every real dwell is below 2^14)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t off = z_offset(draw_word(w, j), class4);
+                    if (z_is_tail(off)) d[j] = (uint32_t)dwell_from_z(z_tail(p.z2, off, blk * 8 + j, key, ST_DWELL_TAIL), p.dwell_mean, p.dwell_std);
+                }
+            }
+            if (nk_tile < TK) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (lane * 8 + j >= nk_tile) d[j] = 0;
+            }
+            if (p.want_ss) {
+                const int64_t ss0 = ss_pos + lane * 8;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (lane * 8 + j < nk_tile) p.ss[ss0 + j] = (int32_t)d[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) sum += d[j];
         }
         uint32_t inc = sum;
 #pragma unroll
@@ -346,57 +361,79 @@ __global__ void __launch_bounds__(256) read_plan_kernel(const __grid_constant__ 
         p.read_n0[r] = n0;
         p.read_offset[r] = off;
         p.read_median[r] = med;
+        ReadRec *rr = p.read_rec + r;   // (sigoff: K3)
+        rr->L = (uint32_t)total;
+        rr->pad0 = 0;
+        rr->offset = off;
+        rr->pad1 = 0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: one CTA — exclusive scan of the 64-sample-aligned read lengths
+// K3: one CTA — exclusive scan of the 64-sample-aligned read lengths, 4096 reads per round (four consecutive reads per
+// thread: coalesced 16-byte loads)
 __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constant__ GenParams p) {
     __shared__ uint64_t s_warp[32];
-    __shared__ uint64_t s_total;
-    const int tid = threadIdx.x;
-    const int per = (p.n_reads + 1023) / 1024;
-    const int lo = min(p.n_reads, tid * per), hi = min(p.n_reads, lo + per);
-    uint64_t part = 0, raw = 0;
-    for (int r = lo; r < hi; r++) {
-        const uint64_t l = p.read_siglen[r];
-        part += (l + 63) & ~63ull;
-        raw += l;
-    }
-    uint64_t inc = part;
+    __shared__ uint64_t s_raw[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t carry = 0, raw_total = 0;
+    for (int r0 = 0; r0 < p.n_reads; r0 += 4096) {
+        const int r = r0 + 4 * tid;
+        uint32_t l[4] = {0, 0, 0, 0};
+        if (r + 3 < p.n_reads) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p.read_siglen + r);   // (cudaMalloc'd, r a multiple of 4)
+            l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
+        } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((tid & 31) >= o) inc += v;
-    }
-    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
-    __syncthreads();
-    if (tid < 32) {
-        uint64_t w = s_warp[tid], winc = w;
+            for (int i = 0; i < 4; i++)
+                if (r + i < p.n_reads) l[i] = p.read_siglen[r + i];
+        }
+        uint64_t al[4], mine = 0, raw = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            al[i] = ((uint64_t)l[i] + 63) & ~63ull;
+            mine += al[i];
+            raw += l[i];
+        }
+        uint64_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, o);
+        __syncthreads();   // (the shared totals of the previous round have been read)
+        if (lane == 31) s_warp[warp] = inc;
+        if (lane == 0) s_raw[warp] = raw;
+        __syncthreads();
+        // every warp scans the 32 warp totals for itself
+        const uint64_t wt = s_warp[lane];
+        uint64_t winc = wt, rawall = s_raw[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint64_t v = __shfl_up_sync(0xffffffffu, winc, o);
-            if (tid >= o) winc += v;
+            if (lane >= o) winc += v;
         }
-        s_warp[tid] = winc - w;
-        if (tid == 31) s_total = winc;
-    }
-    __syncthreads();
-    uint64_t base = s_warp[tid >> 5] + inc - part;
-    for (int r = lo; r < hi; r++) {
-        const uint32_t l = p.read_siglen[r];
-        p.read_sigoff[r] = (int64_t)base;
-        ReadRec rr;
-        rr.sigoff = (int64_t)base; rr.L = l; rr.pad0 = 0; rr.offset = p.read_offset[r]; rr.pad1 = 0;
-        p.read_rec[r] = rr;
-        base += ((uint64_t)l + 63) & ~63ull;
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, o);
-    if (tid == 0) p.meta[1] = 0;
-    __syncthreads();
-    if ((tid & 31) == 0) atomicAdd((unsigned long long *)&p.meta[1], (unsigned long long)raw);
-    if (tid == 0) p.meta[0] = (int64_t)s_total;
+        for (int o = 16; o > 0; o >>= 1) rawall += __shfl_xor_sync(0xffffffffu, rawall, o);
+        const uint64_t before = __shfl_sync(0xffffffffu, winc - wt, warp), all = __shfl_sync(0xffffffffu, winc, 31);
+        uint64_t off = carry + before + inc - mine;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (r + i < p.n_reads) {
+                p.read_sigoff[r + i] = (int64_t)off;
+                p.read_rec[r + i].sigoff = (int64_t)off;   // (L and the ADC offset of the record: K2)
+            }
+            off += al[i];
+        }
+        carry += all;
+        raw_total += rawall;
+    }
+    if (tid == 0) {
+        p.meta[0] = (int64_t)carry;
+        p.meta[1] = (int64_t)raw_total;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

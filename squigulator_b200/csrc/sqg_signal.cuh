@@ -497,10 +497,9 @@ struct TileIn {   // the descriptor fields phase A works from (warp-uniform)
 
 // Phase A of one tile: its k-mers are appended to the run's window.  Descriptor, base window and prefix row are already
 // in the warp's buffer.
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
 __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsigned char *smem, uint32_t map_off, uint32_t wbase, Run &t,
                                               const TileIn &td) {
-    constexpr bool SINGLE = METH || !NOISY;   // one gather per k-mer from a table indexed by rank
     const int nk_tile = td.nk;
     const int nb = nk_tile + p.k - 1;
     const uint32_t dig_off = map_off + W_DIG;
@@ -824,7 +823,7 @@ __device__ __noinline__ void slow_tile(const GenParams &p, const unsigned char *
     }
 }
 
-template <bool NOISY, bool RAND_DWELL, bool METH, bool REV, bool QUAD>
+template <bool NOISY, bool RAND_DWELL, bool METH, bool REV>
 __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_constant__ GenParams p) {
     constexpr bool USE_Z = NOISY;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -948,7 +947,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) signal_kernel(const __grid_cons
                     prefetch_next();
                     break;
                 }
-                register_tile<NOISY, RAND_DWELL, METH, REV, QUAD && !METH>(p, lane, smem, map_off, wbase, t, td);
+                register_tile<NOISY, RAND_DWELL, METH, REV>(p, lane, smem, map_off, wbase, t, td);
                 prefetch_next();
                 t.f_end += td.S;
                 lst = last;
