@@ -24,12 +24,28 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[2] (per-GPU shard; the north_star target is quoted on this profile)
-    "dna-r10-prom": dict(profile="dna-r10-prom", k=9, rna=False, config="configs[2]"),
+    "dna-r10-prom": dict(profile="dna-r10-prom", k=9, rna=False, meth=False, config="configs[2]"),
     # configs[1]
-    "dna-r9-prom": dict(profile="dna-r9-prom", k=6, rna=False, config="configs[1]"),
+    "dna-r9-prom": dict(profile="dna-r9-prom", k=6, rna=False, meth=False, config="configs[1]"),
     # configs[3] shape: whole transcripts, ragged, reversed output, fixed dwell 31
-    "rna004-prom": dict(profile="rna004-prom", k=9, rna=True, config="configs[3]"),
+    "rna004-prom": dict(profile="rna004-prom", k=9, rna=True, meth=False, config="configs[3]"),
+    # configs[4]: CpG-methylation model path - base-5 ranks, the reference's 5^9-entry (15.6 MB) R10 CpG table,
+    # reads with 'M' at methylated CpG sites (synthetic methylation frequency 0.7 per site)
+    "dna-r10-prom-meth": dict(profile="dna-r10-prom", k=9, rna=False, meth=True, config="configs[4]"),
 }
+
+
+def load_model(name, k, meth):
+    """The reference's own built-in table for the workload (oracle/dump_models.py wrote it at build time through the
+    compiled, unmodified reference; plain data, nothing of oracle/ is executed here), else a random-init table of the
+    same shape.  Returns (interleaved float32 table, description)."""
+    p = os.path.join(ROOT, "oracle", "_ref", "models", name + ".f32")
+    n = (5 if meth else 4) ** k
+    if os.path.exists(p):
+        m = np.fromfile(p, dtype=np.float32)
+        if m.size == 2 * n:
+            return m, "the reference's built-in table"
+    return synth_model(n), "random-init table (reference tables not built here)"
 
 
 def synth_model(num_kmer, seed=7):
@@ -39,6 +55,18 @@ def synth_model(num_kmer, seed=7):
     m[0::2] = rs.uniform(60, 130, num_kmer)
     m[1::2] = rs.uniform(1.0, 4.0, num_kmer)
     return m
+
+
+def methylate(bases, off, freq, seed):
+    """CpG sites of every read -> 'M' with probability freq (what methylate_dna(), src/genread.c:207-241, does to reads
+    of a genome whose --meth-freq file gives that frequency at every site)"""
+    rs = np.random.RandomState(seed)
+    b = bases.copy()
+    cg = np.nonzero((b[:-1] == ord("C")) & (b[1:] == ord("G")))[0]
+    ends = off[1:] - 1   # a CG pair must not straddle two reads
+    cg = cg[~np.isin(cg, ends)]
+    b[cg[rs.random_sample(cg.size) < freq]] = ord("M")
+    return b
 
 
 def synth_reads(n_reads, mean_len, rna, seed, genome_mb=64, with_coords=False):
@@ -188,6 +216,8 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
     from squigulator_b200.api import PROFILES
     prof = PROFILES[wl["profile"]][0]
     bases, off, genome, coords = synth_reads(reads_per_step, args.read_len, wl["rna"], seed=1000 + rank, with_coords=True)
+    if wl["meth"]:
+        bases = methylate(bases, off, 0.7, seed=2000 + rank)
     n_reads = len(off) - 1
     first = rank * n_reads  # read-index range of this GPU: the Philox counter makes the job independent of N
     out = {}
@@ -237,7 +267,7 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
     k4_ms = ms_k4 / steps
     # DRAM traffic of one launch from the committed ncu --set full capture of this very configuration, else null
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_signal_kernel_ncu.json")
+    tp = os.path.join(ROOT, "profiles", "r02_signal_kernel_ncu.json")
     if os.path.exists(tp):
         t = json.load(open(tp))
         if t.get("workload") == wl["profile"] and t.get("reads_per_step") == n_reads and t.get("samples") == info["samples"]:
@@ -287,6 +317,20 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
                 finish(t)
             return tot, d2h
 
+        # the ceiling this job can reach: plain cudaMemcpyAsync device -> pinned host, all ranks at once, no kernels
+        ceil_bytes = 1 << 30
+        hsrc = torch.empty(ceil_bytes, dtype=torch.uint8, device=f"cuda:{device}")
+        hdst = torch.empty(ceil_bytes, dtype=torch.uint8, pin_memory=True)
+        hdst.copy_(hsrc, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            hdst.copy_(hsrc, non_blocking=True)
+        barrier()
+        d2h_gbs_rank = 4 * ceil_bytes / max_over_ranks(time.perf_counter() - t0) / 1e9   # per rank, while all ranks copy
+        del hsrc, hdst
+        out["d2h_ceiling"] = {"gbs_per_gpu": d2h_gbs_rank, "gbs_all": d2h_gbs_rank * world,
+                              "how": "4 x 1 GiB cudaMemcpyAsync device -> pinned host on every rank at once (max over ranks)"}
         pipeline(3)
         barrier()
         t0 = time.perf_counter()
@@ -296,6 +340,8 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
         out["e2e"] = {"value": sum_over_ranks(float(tot)) / dt, "unit": "samples/s",
                       "h2d_bytes_per_step": nb + (e_reads * 64), "d2h_bytes_per_step": d2h,
                       "steps": e_steps, "reads_per_step_per_gpu": e_reads, "slots": 3,
+                      "d2h_gbs_per_gpu": d2h * e_steps / dt / 1e9,
+                      "frac_of_d2h_ceiling": d2h * e_steps / dt / 1e9 / d2h_gbs_rank,
                       "api": "sqg_submit/sqg_wait/sqg_release (pinned host bases in, pinned host int16 out)"}
         # the same job with SQG_WANT_SVB: the signal crosses PCIe as slow5lib's svb-zd stream
         pipeline(3, want=2)
@@ -306,6 +352,7 @@ def measure_gpu(args, wl, gen, sq, dist, rank, world, device, reads_per_step, st
         dt = max_over_ranks(time.perf_counter() - t0)
         out["e2e_svb"] = {"value": sum_over_ranks(float(tot)) / dt, "unit": "samples/s",
                           "h2d_bytes_per_step": nb + (e_reads * 64), "d2h_bytes_per_step": d2h, "steps": e_steps,
+                          "frac_of_d2h_ceiling": d2h * e_steps / dt / 1e9 / d2h_gbs_rank,
                           "api": "same call with SQG_WANT_SVB: svb-zd streams (zig-zag delta + StreamVByte, bit-identical to slow5lib's) out"}
         # both ends shrunk: reads named by coordinates against the genome resident in HBM, svb-zd out
         gen.load_genome([genome.tobytes()])
@@ -351,7 +398,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dna-r10-prom", choices=sorted(WORKLOADS))
     ap.add_argument("--reads-per-step", type=int, default=32768, help="reads in the resident batch of each GPU")
-    ap.add_argument("--e2e-reads", type=int, default=4096)
+    ap.add_argument("--e2e-reads", type=int, default=8192)
     ap.add_argument("--read-len", type=int, default=10000)
     ap.add_argument("--cpu-reads", type=int, default=0)
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the CPU baseline")
@@ -380,18 +427,32 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    def make_gen(w):
-        # pore-model table: created on rank 0, broadcast once over NCCL, handed to the library as a device pointer
-        n = 4 ** w["k"]
+    # NUMA: bind this rank's threads to the CPUs next to its GPU before any pinned buffer is touched (first touch decides
+    # where the pages live, and the D2H direction is what bounds the end-to-end figure)
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local))
+        affinity = f"nvml ideal CPUs ({len(os.sched_getaffinity(0))} of {os.cpu_count()})"
+    except Exception as e:  # pragma: no cover
+        affinity = f"not set ({type(e).__name__})"
+
+    table_src = {}
+
+    def make_gen(w, rng_mode=0, name=None):
+        # pore-model table: loaded on rank 0, broadcast once over NCCL, handed to the library as a device pointer
+        name = name or [k for k, v in WORKLOADS.items() if v is w][0]
+        n = (5 if w["meth"] else 4) ** w["k"]
         t = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{local}")
         if rank == 0:
-            t.copy_(torch.from_numpy(synth_model(n)))
+            m, table_src[name] = load_model(name, w["k"], w["meth"])
+            t.copy_(torch.from_numpy(m))
         if world > 1:
             dist.broadcast(t, src=0)
         torch.cuda.synchronize()
         prof, flags = PROFILES[w["profile"]]
-        return sq.SignalGenerator(dict(prof), None, w["k"], flags=flags, seed=1, device=local, n_slots=3,
-                                  device_model_ptr=t.data_ptr()), t
+        return sq.SignalGenerator(dict(prof), None, w["k"], flags=flags, seed=1, device=local, n_slots=3, meth=w["meth"],
+                                  rng_mode=rng_mode, device_model_ptr=t.data_ptr()), t
 
     gen, _keep = make_gen(wl)
     res = measure_gpu(args, wl, gen, sq, dist, rank, world, local, args.reads_per_step, args.steps, args.warmup)
@@ -399,6 +460,28 @@ def main():
     store_ms = gen.bench_store(8 << 30, 5)
     store_ms = gen.bench_store(8 << 30, 10)
     res["store_only_gbs"] = (8 << 30) * 10 / (store_ms * 1e-3) / 1e9
+
+    # ---- N GPUs produce exactly the one-GPU output: every rank generates its shard of ONE common read list, rank 0 also
+    # the whole list, per-read digests are compared (outside every timed region) ----
+    shard_equal = None
+    if world > 1:
+        import hashlib
+        from squigulator_b200.shard import shard_range
+        cb, co = synth_reads(64 * world, 3000, wl["rna"], seed=4242, genome_mb=8)
+        if wl["meth"]:
+            cb = methylate(cb, co, 0.7, seed=4243)
+        nr = len(co) - 1
+        lo, hi = shard_range(nr, rank, world)
+        raw = cb.tobytes()
+        mine = gen.gen_batch([raw[co[i]:co[i + 1]] for i in range(lo, hi)], first_read_index=lo)
+        dig = [(lo + i, hashlib.sha256(r["sig"].tobytes()).hexdigest(), r["offset"]) for i, r in enumerate(mine)]
+        allv = [None] * world
+        dist.all_gather_object(allv, dig)
+        if rank == 0:
+            whole = gen.gen_batch([raw[co[i]:co[i + 1]] for i in range(nr)], first_read_index=0)
+            exp = {i: (hashlib.sha256(r["sig"].tobytes()).hexdigest(), r["offset"]) for i, r in enumerate(whole)}
+            got = {i: (h, o) for part in allv for (i, h, o) in part}
+            shard_equal = len(got) == nr and all(got[i] == exp[i] for i in range(nr))
     gen.close()
 
     extra = {}
@@ -413,7 +496,21 @@ def main():
             g2.close()
             extra[name] = {"config": w2["config"], "value": r2["value"], "ms_per_step": r2["ms_per_step"],
                            "roofline_frac": r2["roofline"]["frac"], "kernel_ms": r2["roofline"]["kernel_ms"],
-                           "samples_per_step_per_gpu": r2["samples_per_step_per_gpu"]}
+                           "samples_per_step_per_gpu": r2["samples_per_step_per_gpu"], "table": table_src.get(name)}
+        # SQG_RNG_LEGACY (the reference's own minstd streams by jump-ahead: the parity instrument, not the fast path),
+        # whole path, same metric - so that its cost is on record
+        wl9 = WORKLOADS["dna-r9-prom"]
+        g3, _k3 = make_gen(wl9, rng_mode=1, name="dna-r9-prom")
+        lb, lo_ = synth_reads(512, args.read_len, False, seed=77 + rank, genome_mb=8)
+        raw = lb.tobytes()
+        reads = [raw[lo_[i]:lo_[i + 1]] for i in range(len(lo_) - 1)]
+        g3.gen_batch(reads[:32], first_read_index=0)
+        barrier_t0 = time.perf_counter()
+        rr = g3.gen_batch(reads, first_read_index=0)
+        dt = time.perf_counter() - barrier_t0
+        g3.close()
+        extra["legacy-rng dna-r9-prom"] = {"config": "configs[1] profile, SQG_RNG_LEGACY, host buffers in and out (one synchronous batch of 512 reads)",
+                                           "value": sum(len(r["sig"]) for r in rr) / dt, "unit": "samples/s per GPU"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_extra:
@@ -431,13 +528,15 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "gbases_per_s": res["value"] / prof["dwell_mean"] / 1e9,
                 "config": {"workload": f"{wl['config']} per-GPU shard: -x {wl['profile']}, reads cut (gamma length, mean {args.read_len}) "
-                                       f"from a synthetic iid ACGT genome, random-init {wl['k']}-mer table; step = one resident batch",
+                                       f"from a synthetic iid ACGT genome, {wl['k']}-mer table; step = one resident batch",
                            "reads_per_step_per_gpu": res["reads_per_step_per_gpu"],
                            "samples_per_step_per_gpu": res["samples_per_step_per_gpu"],
                            "l2": "output per step (GBs) far exceeds the 126 MB L2; no flush needed",
+                           "table": table_src.get(args.workload), "cpu_affinity": affinity,
                            "rng": "philox4x32-7", "parallelism": f"reads sharded over {world} GPU(s), no hot-path collective"},
                 "clocks": res["clocks"], "e2e": res.get("e2e"), "e2e_svb": res.get("e2e_svb"), "e2e_coords_svb": res.get("e2e_coords_svb"), "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "cpu_baseline": cpu, "store_only_gbs": res["store_only_gbs"],
+                "d2h_ceiling": res.get("d2h_ceiling"), "shard_equal": shard_equal,
                 "wall_s_timed_region": res["wall_s"], "other_workloads": extra}
         emit_json(line)
     if world > 1:

@@ -445,7 +445,9 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                     uint32_t x = w[e >> 1];
                     d10 = (e & 1) ? (x >> 17) & 0x3FFu : (x >> 7) & 0x3FFu;
                 }
-                uint32_t h = ((Cq >> 5) * 0x9E3779B1u + r_lo * 0x85EBCA6Bu) >> 27;
+                uint32_t h = (Cq >> 5) * 0x9E3779B1u + r_lo * 0x85EBCA6Bu; /* one xorshift-multiply round, top five bits */
+                h ^= h >> 15;
+                h = (h * 0x2C1B3C6Du) >> 27;
                 float z = sqo_z32(o->zt, (d10 << 5) | (l ^ h), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
                 raw[n] = to_i16_f(fma_rz(z, A, Bq));
             }

@@ -941,14 +941,16 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
         CU(cudaGetLastError());
         ctx->base.model_am = ctx->d_model_am.p;
     }
-    if (!ctx->meth && !ctx->legacy && ctx->noisy) {
+    if (!ctx->legacy && ctx->noisy) {
         // the same, indexed by (k+1)-mer: one 16-byte gather serves two consecutive k-mers (pair_model_kernel)
-        const uint64_t n_pair = 4ull * n;
+        const uint64_t n_pair = (ctx->meth ? 5ull : 4ull) * n;
         if (n_pair * sizeof(float4) > (256ull << 20)) return fail(ctx, SQG_ERR_ARG, "k-mer size too large for the paired model table");
-        CU(ctx->d_pair_model.ensure((size_t)n_pair));
-        pair_model_kernel<<<(unsigned)((n_pair + 255) / 256), 256>>>(ctx->d_model_am.p, ctx->d_pair_model.p, (uint32_t)n_pair, ctx->base.kmask);
+        // (+8: a pair whose second k-mer lies past its tile is addressed with one digit of whatever follows the window)
+        CU(ctx->d_pair_model.ensure((size_t)n_pair + 8));
+        CU(cudaMemset(ctx->d_pair_model.p + n_pair, 0, 8 * sizeof(float4)));
+        if (ctx->meth) pair_model5_kernel<<<(unsigned)((n_pair + 255) / 256), 256>>>(ctx->d_model_am.p, ctx->d_pair_model.p, (uint32_t)n_pair, ctx->base.pow5k);
+        else pair_model_kernel<<<(unsigned)((n_pair + 255) / 256), 256>>>(ctx->d_model_am.p, ctx->d_pair_model.p, (uint32_t)n_pair, ctx->base.kmask);
         CU(cudaGetLastError());
-        CU(cudaDeviceSynchronize());
         ctx->base.pair_model = ctx->d_pair_model.p;
     }
     CU(cudaDeviceSynchronize());

@@ -152,6 +152,14 @@ __global__ void __launch_bounds__(256) pair_model_kernel(const float2 *__restric
     const float2 a = am[i >> 2], b = am[i & kmask];
     pair[i] = make_float4(a.x, a.y, b.x, b.y);
 }
+// base-5 (CpG) models: the (k+1)-mer of digits d0..dk has rank i = sum d_j 5^(k-j); its k-mers are i / 5 and i mod 5^k.
+// 5^10 x 16 B = 156 MB for 9-mers, of which reads touch only the entries consistent with "M stands before G" (~25 MB).
+__global__ void __launch_bounds__(256) pair_model5_kernel(const float2 *__restrict__ am, float4 *__restrict__ pair, uint32_t n_pair, uint32_t pow5k) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pair) return;
+    const float2 a = am[i / 5u], b = am[i % pow5k];
+    pair[i] = make_float4(a.x, a.y, b.x, b.y);
+}
 
 // ------------------------------------------------------------------------------------------------
 // K0: tile descriptors (one warp per segment, one lane per tile)

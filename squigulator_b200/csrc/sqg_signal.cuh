@@ -123,9 +123,13 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t off) {
 //   g = 0: word e/2 of A, field F0 (e even) or F1 (e odd)        g = 2: the same of B
 //   g = 1: field F2 of word e of A (e < 4) or of word e - 4 of B (e >= 4)
 // A lane of the signal kernel handles the three chunks l, 32 + l, 64 + l of a unit with two Philox calls.  The draw's
-// table CLASS is l ^ h, h = five hash bits of the chunk's group of 32 (and of the read): within a group the classes are a
+// table CLASS is l ^ h, h = five hash bits (amp_mix) of the chunk's group of 32 (and of the read): within a group the classes are a
 // bijection of the lanes - one bank per lane - and over the groups every position of the signal meets every class.
-__device__ __forceinline__ uint32_t amp_class_hash(uint32_t group, uint32_t hmul) { return (group * 0x9E3779B1u + hmul) >> 27; }
+__device__ __forceinline__ uint32_t amp_mix(uint32_t x) {   // x = group * 0x9E3779B1 + amp_hmul(read): one xorshift-multiply round
+    x ^= x >> 15;
+    return (x * 0x2C1B3C6Du) >> 27;
+}
+__device__ __forceinline__ uint32_t amp_class_hash(uint32_t group, uint32_t hmul) { return amp_mix(group * 0x9E3779B1u + hmul); }
 __device__ __forceinline__ uint32_t amp_class4(uint32_t Cq, uint32_t hmul) { return ((Cq & 31u) ^ amp_class_hash(Cq >> 5, hmul)) << 2; }
 __device__ __forceinline__ uint32_t amp_hmul(uint32_t r_lo) { return r_lo * 0x85EBCA6Bu; }
 // a field moved to bits 7..16, where z_offset() masks it: F1 by a multiply-high (x >> 10 on the FMA pipe, which has
@@ -396,7 +400,7 @@ __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigne
         else if (i == 1) amp_fields<1>(A, B, dw);
         else amp_fields<REV ? 0 : 2>(A, B, dw);
         const uint32_t Hi = REV ? H - (uint32_t)i * 0x9E3779B1u : H + (uint32_t)i * 0x9E3779B1u;   // (warp-uniform)
-        const uint32_t class4 = lc.lane4 ^ ((Hi >> 27) << 2);
+        const uint32_t class4 = lc.lane4 ^ (amp_mix(Hi) << 2);
         bad[i] = fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, p.l2_vote != 0, true, pk[i]);
     }
 #pragma unroll
@@ -512,7 +516,7 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
     // other byte in the tile (IUPAC codes, U, N: src/seq.h:14-28 folds them) sends the whole warp through the
     // 256-entry code table, which is also the path of base-5 (CpG) models (src/seq.h:45-60) and of prefix junctions.
     uint32_t dg[4] = {0, 0, 0, 0};   // the lane's 16 digits, one per byte
-    bool table_path = METH || tile_is_junction(p, td.a_rem, nk_tile);
+    bool table_path = tile_is_junction(p, td.a_rem, nk_tile);
     if (!table_path) {
         const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(p.bases + (td.a_rem > 0 ? td.a_off : td.b_off)) & 15u);
         const uint32_t s0 = shift + 8u * (uint32_t)lane;     // lane's first byte within the raw buffer
@@ -522,33 +526,40 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
         const uint32_t q0 = hi ? w0.y : w0.x, q1 = hi ? w1.x : w0.y, q2 = hi ? w1.y : w1.x, q3 = hi ? w2.x : w1.y, q4 = hi ? w2.y : w2.x;
         const uint32_t fs = 8u * (s0 & 3u);
         const uint32_t x[4] = {__funnelshift_r(q0, q1, fs), __funnelshift_r(q1, q2, fs), __funnelshift_r(q2, q3, fs), __funnelshift_r(q3, q4, fs)};
+        // base 4: ACGTacgt -> ((c>>1) ^ (c>>2)) & 3, checked by mapping the digits back ("ACGT" by PRMT) against the byte
+        // with its case bit cleared.  Base 5 (src/seq.h:45-60, upper case only): A C G M T = 41 43 47 4D 54 ->
+        // b1 + (b1 & b2) + 3 b3 + 4 b4 (b_i = bit i of the byte) = 0 1 2 3 4, checked against "ACGMT" exactly.
+        auto digits_of = [&](uint32_t w) -> uint32_t {
+            if (!METH) return ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+            const uint32_t b1 = (w >> 1) & 0x01010101u, b2 = (w >> 2) & 0x01010101u, b3 = (w >> 3) & 0x01010101u, b4 = (w >> 4) & 0x01010101u;
+            return b1 + (b1 & b2) + 3u * b3 + 4u * b4;
+        };
+        auto check_of = [&](uint32_t c, uint32_t w) -> uint32_t {
+            const uint32_t u = (c | (c >> 4)) & 0x00FF00FFu;
+            const uint32_t sel = (u | (u >> 8)) & 0xFFFFu;                    // the four digits as PRMT selectors
+            return METH ? (__byte_perm(0x4D474341u /* "ACGM" */, 0x00000054u /* "T" */, sel) ^ w)
+                        : (__byte_perm(0x54474341u /* "ACGT" */, 0u, sel) ^ (w & 0xDFDFDFDFu));
+        };
         uint32_t bad = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t c = ((x[i] >> 1) ^ (x[i] >> 2)) & 0x03030303u;
-            const uint32_t u = (c | (c >> 4)) & 0x00FF00FFu;
-            const uint32_t sel = (u | (u >> 8)) & 0xFFFFu;                    // the four digits as PRMT selectors
-            bad |= __byte_perm(0x54474341u /* "ACGT" */, 0u, sel) ^ (x[i] & 0xDFDFDFDFu);
-            dg[i] = c;
+            dg[i] = digits_of(x[i]);
+            bad |= check_of(dg[i], x[i]);
         }
-        // bytes past the window's end are whatever the 16-byte granules held: harmless as digits, but they must not
-        // force the table path, so only the lane's bytes inside the window count
+        // bytes past the window's end are whatever the 16-byte granules held: they must not force the table path, so
+        // only the lane's bytes inside the window count - and their digits are cleared (base 5: such a "digit" can exceed
+        // 4, and the pair rank of the tile's last k-mer takes one digit from behind the window)
         const int inside = nb - 8 * lane;
         if (inside < 16) {
-            if (inside <= 0) bad = 0;
-            else {
-                uint32_t keep = 0;
+            uint32_t keep = 0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int nbytes = min(max(inside - 4 * i, 0), 4);
-                    const uint32_t m = nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
-                    const uint32_t c = dg[i];
-                    const uint32_t u = (c | (c >> 4)) & 0x00FF00FFu;
-                    const uint32_t sel = (u | (u >> 8)) & 0xFFFFu;
-                    keep |= (__byte_perm(0x54474341u, 0u, sel) ^ (x[i] & 0xDFDFDFDFu)) & m;
-                }
-                bad = keep;
+            for (int i = 0; i < 4; i++) {
+                const int nbytes = min(max(inside - 4 * i, 0), 4);
+                const uint32_t m = nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+                keep |= check_of(dg[i], x[i]) & m;
+                dg[i] &= m;
             }
+            bad = keep;
         }
         table_path = __any_sync(0xffffffffu, bad != 0);
     }
@@ -571,10 +582,18 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
             }
         }
         __syncwarp();
-        // (digits past the window are stale bytes of an earlier tile: they only reach k-mers past the tile's end)
         const uint2 dwa = *reinterpret_cast<const uint2 *>(smem + dig_off + m0);
         const uint2 dwb = *reinterpret_cast<const uint2 *>(smem + dig_off + m0 + 8);
         dg[0] = dwa.x; dg[1] = dwa.y; dg[2] = dwb.x; dg[3] = dwb.y;
+        // (what lies behind the window in this buffer is raw bytes, not digits: cleared, as on the arithmetic path)
+        const int inside = nb - 8 * lane;
+        if (inside < 16) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int nbytes = min(max(inside - 4 * i, 0), 4);
+                dg[i] &= nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+            }
+        }
         __syncwarp();   // (the digit buffer is rewritten by this warp's next tile)
     }
 
@@ -588,31 +607,24 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
     float2 mv[8];
     const uint32_t par_w = map_off + W_PAR + 8 * (uint32_t)(t.nreg + m0);
     const uint32_t par_a = wbase + W_PAR + 8 * (uint32_t)(t.nreg + m0);   // (the same, as an address for the asynchronous copies)
-    uint32_t ranks[8];
+    const bool pairs = NOISY && (t.nreg & 1) == 0;   // (16-byte copies need an even window position)
+    uint32_t ranks[8], pr[4];
     if (!METH) {
         const uint32_t P = ((((dg[0] & 0x03030303u) * 0x40100401u) >> 24) << 24) | ((((dg[1] & 0x03030303u) * 0x40100401u) >> 24) << 16) |
                            ((((dg[2] & 0x03030303u) * 0x40100401u) >> 24) << 8) | (((dg[3] & 0x03030303u) * 0x40100401u) >> 24);
-        if (NOISY && (t.nreg & 1) == 0) {
+        if (pairs) {
             const int sh0 = 30 - 2 * p.k;                 // 32 - 2(k+1)
             const uint32_t pmask = (p.kmask << 2) | 3u;   // 4^(k+1) - 1
-            // (the 16-byte shared-memory writes of these copies collide in the banks - lane stride 64 bytes - but visiting the
-            // pairs in a rotated order to avoid that costs more in instructions than the replays do: measured)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t r = (P >> (sh0 - 4 * j)) & pmask;
-#ifdef SQG_KO_GATHER
-                if (m0 + 2 * j < nk_tile) cp_async16(par_a + 16 * j, &p.pair_model[(td.nk & 0xFF) * 128 + j * 32 + lane]);   // coalesced (timing only)
-#else
-                if (m0 + 2 * j < nk_tile) cp_async16(par_a + 16 * j, &p.pair_model[r]);
-#endif
-            }
+            for (int j = 0; j < 4; j++) pr[j] = (P >> (sh0 - 4 * j)) & pmask;
         } else {
             const int sh0 = 32 - 2 * p.k;
 #pragma unroll
             for (int j = 0; j < 8; j++) ranks[j] = (P >> (sh0 - 2 * j)) & p.kmask;
         }
     } else {
-        // base-5 (CpG) ranks, src/seq.h:62-74, rolled: rank' = 5*rank - 5^k*(leading digit) + (new digit)
+        // base-5 (CpG) ranks, src/seq.h:62-74, rolled: rank' = 5*rank - 5^k*(leading digit) + (new digit); the (k+1)-mer
+        // at an even position = 5 * (its first k-mer) + (the digit behind it)
         const uint32_t dw[4] = {dg[0], dg[1], dg[2], dg[3]};
         const int km1 = p.k - 1;
         uint32_t rank = 0;
@@ -625,12 +637,24 @@ __device__ __forceinline__ void register_tile(const GenParams &p, int lane, unsi
             const uint32_t word = bi < 4 ? dw[0] : bi < 8 ? dw[1] : bi < 12 ? dw[2] : dw[3];
             rank = rank * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);             // k digits: the k-mer at lane position j
             ranks[j] = rank;
+            if (j & 1) pr[j >> 1] = ranks[j - 1] * 5 + ((word >> (8 * (bi & 3))) & 0xFFu);
             rank -= ((dw[j >> 2] >> (8 * (j & 3))) & 0xFFu) * p.kmask;        // drop its leading digit (kmask = 5^(k-1))
         }
     }
-    if (METH || !NOISY || (t.nreg & 1) != 0) {
-        // one gather per k-mer, by rank: CpG models, ideal amplitudes, and a window position the 16-byte copies cannot take
-        // (a second segment behind an odd number of k-mers)
+    if (pairs) {
+        // (the 16-byte shared-memory writes of these copies collide in the banks - lane stride 64 bytes - but visiting the
+        // pairs in a rotated order to avoid that costs more in instructions than the replays do: measured)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#ifdef SQG_KO_GATHER
+            if (m0 + 2 * j < nk_tile) cp_async16(par_a + 16 * j, &p.pair_model[(td.nk & 0xFF) * 128 + j * 32 + lane]);   // coalesced (timing only)
+#else
+            if (m0 + 2 * j < nk_tile) cp_async16(par_a + 16 * j, &p.pair_model[pr[j]]);
+#endif
+        }
+    } else {
+        // one gather per k-mer, by rank: ideal amplitudes (the raw table, double arithmetic below), and a window position
+        // the 16-byte copies cannot take (a second segment behind an odd number of k-mers)
         if (NOISY) {
 #pragma unroll
             for (int j = 0; j < 8; j++)

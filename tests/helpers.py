@@ -178,6 +178,12 @@ def golden_paths():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+def real_model(name):
+    """The reference's built-in table `name` (oracle/dump_models.py wrote it through the compiled reference), or None."""
+    p = os.path.join(ORACLE_DIR, "_ref", "models", name + ".f32")
+    return np.fromfile(p, dtype=np.float32) if os.path.exists(p) else None
+
+
 def random_model(num_kmer, seed=7):
     """Synthetic pore model of the right shape: level_mean ~ U(60,130) pA, level_stdv ~ U(1,4) pA."""
     rs = np.random.RandomState(seed)

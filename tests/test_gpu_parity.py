@@ -68,6 +68,24 @@ def test_gpu_equals_oracle(case, sq, oracle_lib, ztable):
     run_pair(sq, oracle_lib, ztable, prof, pflags | xflags, k, reads, meth=meth, first=1000)
 
 
+REAL = [("dna-r9-prom", "dna-r9-prom", 6, False, b"ACGT"), ("dna-r10-prom", "dna-r10-prom", 9, False, b"ACGT"),
+        ("rna004-prom", "rna004-prom", 9, False, b"ACGT"), ("rna-r9-prom", "rna-r9-prom", 5, False, b"ACGT"),
+        ("dna-r9-prom-meth", "dna-r9-prom", 6, True, b"ACGTM"), ("dna-r10-prom-meth", "dna-r10-prom", 9, True, b"ACGTM")]
+
+
+@pytest.mark.parametrize("case", REAL, ids=[c[0] for c in REAL])
+def test_gpu_equals_oracle_with_the_reference_tables(case, sq, oracle_lib, ztable):
+    """Philox mode with the reference's own built-in pore models (src/model.h, src/methmodel.c; dumped at build time by
+    oracle/dump_models.py through the compiled reference) instead of a random table."""
+    name, preset, k, meth, alpha = case
+    model = H.real_model(name)
+    if model is None:
+        pytest.skip("oracle/_ref/models not built (needs /root/reference at build time)")
+    prof, pflags = H.PRESETS[preset]
+    reads = H.random_reads(24, 2500, seed=hash(name) & 0xFFFF, alphabet=alpha)
+    run_pair(sq, oracle_lib, ztable, prof, pflags, k, reads, meth=meth, first=31, model=model)
+
+
 def test_edge_cases(sq, oracle_lib, ztable):
     prof, pflags = H.PRESETS["dna-r10-prom"]
     # empty read, reads shorter than k (the "ACGTACGTACGT" rule, reference src/gensig.c:242-245), len == k, len == k+1
