@@ -108,6 +108,13 @@ void sqg_host_free(void *p);
                              slow5_ptr_compress_solo(SLOW5_COMPRESS_SVB_ZD, raw_signal, ...) gives
                              (slow5lib/src/slow5_press.c:1055-1087) - INSTEAD of raw int16: `signal` is NULL,
                              `svb`/`svb_off` are set; ~1.3 bytes per sample cross PCIe instead of 2 */
+#define SQG_WANT_RECORDS 0x10u /* return every read as a finished BLOW5 RECORD - exactly the bytes slow5_rec_to_mem()
+                                  (slow5lib/src/slow5.c:3815-4010) makes of it for a file opened with
+                                  slow5_set_press(sp, SLOW5_COMPRESS_NONE, SLOW5_COMPRESS_SVB_ZD): record size, read id,
+                                  primary fields, svb-zd signal, the auxiliary fields squigulator sets
+                                  (src/gensig.c:130-217) - all records back to back in `svb` (svb_off / svb_len per
+                                  record), so that the host's part of writing a batch is ONE slow5_write_bytes /
+                                  fwrite.  Set by sqg_gen_batch_records / sqg_submit_records, which take the ids. */
 #define SQG_WANT_SS_TEXT 0x4u /* return aln->ss already formatted as the PAF/SAM `ss:Z:` value: "d0,d1,...,dn-1," per read
                                  (no terminator), RNA reads last k-mer first, exactly what src/format.c:69-75 appends */
 
@@ -121,8 +128,8 @@ typedef struct {
     const double *median_before;   /* n_reads                         (src/gensig.c:317) */
     const int32_t *ss;             /* SQG_WANT_SS: dwell per k-mer, read i at ss[ss_off[i] .. ss_off[i+1]) */
     const int64_t *ss_off;         /* n_reads+1 */
-    const uint8_t *svb;            /* SQG_WANT_SVB: read i's stream = svb[svb_off[i] .. svb_off[i] + svb_len[i]) */
-    const int64_t *svb_off;        /* n_reads+1 (16-byte aligned starts; [n_reads] = bytes copied) */
+    const uint8_t *svb;            /* SQG_WANT_SVB: read i's stream (SQG_WANT_RECORDS: its record) = svb[svb_off[i] .. + svb_len[i]) */
+    const int64_t *svb_off;        /* n_reads+1 (streams / records back to back; [n_reads] = bytes copied) */
     const int64_t *svb_len;        /* n_reads */
     const char *ss_text;           /* SQG_WANT_SS_TEXT: read i's dwell string = ss_text[ss_text_off[i] .. ss_text_off[i+1]) */
     const int64_t *ss_text_off;    /* n_reads+1 */
@@ -138,6 +145,21 @@ typedef struct {
 int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
                   int64_t first_read_index, uint32_t want, sqg_result_t *res);
 
+/* ---- finished BLOW5 records (replaces set_record_*_fields + slow5_encode, src/sim.c:603-611) ----
+ * What only the host knows about the records of a batch: the read ids (src/sim.c:564-570), the samples generated before
+ * the batch (aux start_time continues from there in read order, src/sim.c:602) and whether --ont-friendly added the
+ * end_reason field.  aux read_number of read i is first_read_index + i (src/sim.c:604).  The arrays must stay valid
+ * until the batch is done (sqg_wait for submitted batches). */
+typedef struct {
+    const char *read_ids;   /* ids back to back, no terminators: read i = read_ids[id_off[i] .. id_off[i+1]) */
+    const int64_t *id_off;  /* n_reads+1 */
+    uint64_t start_time0;   /* core->n_samples before the batch */
+    int32_t ont_friendly;   /* non-zero: records carry end_reason = 0 (src/gensig.c:211-217) */
+    int32_t reserved;
+} sqg_record_info_t;
+int sqg_gen_batch_records(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                          int64_t first_read_index, const sqg_record_info_t *rec, uint32_t want, sqg_result_t *res);
+
 /* ---- asynchronous dispatcher: CUDA-stream slots instead of src/thread.c's pthread pool ----
  * sqg_submit returns as soon as the batch is queued on a free slot (it blocks only while all
  * n_slots are in flight); the inputs must stay valid until sqg_wait returns.  One submitter thread;
@@ -148,6 +170,8 @@ int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int6
 typedef int64_t sqg_ticket_t;
 int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
                int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket);
+int sqg_submit_records(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                       int64_t first_read_index, const sqg_record_info_t *rec, uint32_t want, sqg_ticket_t *ticket);
 int sqg_wait(sqg_ctx_t *ctx, sqg_ticket_t ticket, sqg_result_t *res);
 int sqg_release(sqg_ctx_t *ctx, sqg_ticket_t ticket);
 

@@ -247,3 +247,45 @@ int32_t sqref_gen_read(void *hv, int32_t *contig, int32_t *ref_pos, char *strand
         if (core->ref->ref_names[c] == rid) *contig = c;
     return rlen;
 }
+
+/* ---- BLOW5 records by the reference's own code: slow5_open + set_header_attributes / set_header_aux_fields
+ * (src/gensig.c:80-168) + slow5_set_press(NONE, SVB_ZD) + slow5_hdr_write; then per read set_record_primary_fields /
+ * set_record_aux_fields (src/gensig.c:171-217) + slow5_encode (slow5lib/src/slow5.c).  For tests/test_records.py. ---- */
+void set_header_attributes(slow5_file_t *sp, int8_t rna, int8_t r10, double sample_frequency);
+void set_header_aux_fields(slow5_file_t *sp, int8_t ont_friendly);
+void set_record_primary_fields(profile_t *profile, slow5_rec_t *slow5_record, char *read_id, double offset, int64_t len_raw_signal, int16_t *raw_signal);
+void set_record_aux_fields(slow5_rec_t *slow5_record, slow5_file_t *sp, double median_before, int32_t read_number, uint64_t start_time, int8_t ont_friendly);
+
+void *sqref_rec_open(const char *path, const profile_t *p, uint32_t flags, int ont) {
+    slow5_file_t *sp = slow5_open(path, "w");
+    if (!sp) return NULL;
+    set_header_attributes(sp, flags & SQ_RNA ? 1 : 0, flags & SQ_R10 ? 1 : 0, p->sample_rate);
+    set_header_aux_fields(sp, ont ? 1 : 0);
+    if (slow5_set_press(sp, SLOW5_COMPRESS_NONE, SLOW5_COMPRESS_SVB_ZD) < 0) return NULL;
+    if (slow5_hdr_write(sp) < 0) return NULL;
+    return sp;
+}
+
+/* the record of one read as slow5_encode makes it; returns its size (or -1), copies at most cap bytes to out */
+int64_t sqref_rec_encode(void *spv, const profile_t *p, const char *read_id, double offset, const int16_t *sig, int64_t n,
+                         double median_before, int32_t read_number, uint64_t start_time, int ont, uint8_t *out, int64_t cap) {
+    slow5_file_t *sp = (slow5_file_t *)spv;
+    slow5_rec_t *rec = slow5_rec_init();
+    char *id = strdup(read_id);
+    int16_t *raw = (int16_t *)malloc(sizeof(int16_t) * (size_t)(n > 0 ? n : 1));
+    memcpy(raw, sig, sizeof(int16_t) * (size_t)n);
+    profile_t prof = *p;
+    set_record_primary_fields(&prof, rec, id, offset, n, raw);
+    set_record_aux_fields(rec, sp, median_before, read_number, start_time, ont ? 1 : 0);
+    void *mem = NULL;
+    size_t bytes = 0;
+    if (slow5_encode(&mem, &bytes, rec, sp) < 0) return -1;
+    if ((int64_t)bytes <= cap) memcpy(out, mem, bytes);
+    free(mem);
+    slow5_rec_free(rec);
+    return (int64_t)bytes;
+}
+
+/* records made elsewhere (the GPU), written as they are */
+int sqref_rec_write_bytes(void *spv, const void *mem, int64_t bytes) { return slow5_write_bytes((void *)mem, (size_t)bytes, (slow5_file_t *)spv); }
+int sqref_rec_close(void *spv) { return slow5_close((slow5_file_t *)spv); }

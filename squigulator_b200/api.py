@@ -13,6 +13,7 @@ WANT_SS = 0x1
 WANT_SVB = 0x2
 WANT_BASES = 0x8
 WANT_SS_TEXT = 0x4
+WANT_RECORDS = 0x10
 
 PROFILE_FIELDS = ("digitisation", "sample_rate", "bps", "range", "offset_mean", "offset_std",
                   "median_before_mean", "median_before_std", "dwell_mean", "dwell_std")
@@ -64,6 +65,12 @@ class Result(C.Structure):
                 ("bases", C.POINTER(C.c_char)), ("bases_off", C.POINTER(C.c_int64)), ("meth_draws", C.c_int64)]
 
 
+class RecordInfo(C.Structure):
+    """== sqg_record_info_t"""
+    _fields_ = [("read_ids", C.c_void_p), ("id_off", C.c_void_p), ("start_time0", C.c_uint64), ("ont_friendly", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 # == sqg_coord_t, as a numpy record (one row per read)
 COORD_DTYPE = np.dtype([("contig", np.int32), ("len", np.int32), ("pos", np.int64), ("strand", np.int32),
                         ("reserved", np.int32)])
@@ -85,6 +92,8 @@ _SIGNATURES = {
     "sqg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "sqg_host_free": (None, [C.c_void_p]),
     "sqg_gen_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.POINTER(Result)]),
+    "sqg_gen_batch_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(RecordInfo), C.c_uint32, C.POINTER(Result)]),
+    "sqg_submit_records": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(RecordInfo), C.c_uint32, C.POINTER(C.c_int64)]),
     "sqg_submit": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.POINTER(C.c_int64)]),
     "sqg_genome_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqg_gen_batch_coords": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.POINTER(Result)]),
@@ -212,6 +221,19 @@ class SignalGenerator:
                                            first_read_index, (WANT_SS if want_ss else 0) | (WANT_SVB if want_svb else 0) | (WANT_SS_TEXT if want_ss_text else 0),
                                            C.byref(res)))
         return self._unpack(res)
+
+    def gen_batch_records(self, reads, read_ids, first_read_index=0, start_time0=0, ont_friendly=False):
+        """finished BLOW5 records (record compression NONE, signal svb-zd): returns (bytes of all records back to back,
+        per-read dicts with 'svb' = the record of the read)"""
+        bases, off = _pack_reads(reads)
+        ids, ioff = _pack_reads([i if isinstance(i, bytes) else i.encode() for i in read_ids])
+        info = RecordInfo(ids.ctypes.data, ioff.ctypes.data, start_time0, 1 if ont_friendly else 0, 0)
+        res = Result()
+        self._check(self.lib.sqg_gen_batch_records(self.h, len(reads), bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                                   first_read_index, C.byref(info), 0, C.byref(res)))
+        total = int(res.svb_off[res.n_reads]) if res.n_reads else 0
+        blob = C.string_at(res.svb, total) if total else b""
+        return blob, self._unpack(res)
 
     def gen_batch_raw(self, bases, off, first_read_index=0, want=0):
         """host numpy buffers in, sqg_result_t (views into pinned memory) out — what bench.py's e2e leg times"""

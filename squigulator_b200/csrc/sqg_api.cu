@@ -124,8 +124,14 @@ struct Slot {
     DevBuf<double> d_offset, d_median;
     DevBuf<int16_t> d_sig;
     DevBuf<int32_t> d_ss;
-    DevBuf<int64_t> d_svb_len, d_svb_off;   // SQG_WANT_SVB
+    DevBuf<int64_t> d_svb_len, d_svb_off;   // SQG_WANT_SVB / SQG_WANT_RECORDS (sqg_svb.cuh)
     DevBuf<uint8_t> d_svb;
+    DevBuf<int64_t> d_seg0, d_fixed, d_svb_tot, d_id_off;
+    DevBuf<unsigned long long> d_seg_state, d_seg_excl, d_read_d0;
+    DevBuf<unsigned int> d_ticket;
+    DevBuf<char> d_ids;
+    PinBuf<int64_t> h_svb_tot;
+    const sqg_record_info_t *rec_info = nullptr;   // SQG_WANT_RECORDS: ids and aux constants of the batch in flight
     PinBuf<int64_t> h_svb_len, h_svb_off;
     PinBuf<uint8_t> h_svb;
     int64_t svb_bytes = 0;
@@ -172,6 +178,8 @@ struct Slot {
         h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
         h_ss.release();
         d_svb_len.release(); d_svb_off.release(); d_svb.release(); h_svb_len.release(); h_svb_off.release(); h_svb.release();
+        d_seg0.release(); d_fixed.release(); d_svb_tot.release(); d_id_off.release(); d_seg_state.release(); d_seg_excl.release();
+        d_read_d0.release(); d_ticket.release(); d_ids.release(); h_svb_tot.release();
         d_sst_len.release(); d_sst_off.release(); d_ss_off.release(); d_sst.release(); h_sst_off.release(); h_sst.release();
         d_pieces.release(); h_pieces.release();
         d_coords.release(); d_out_off.release(); d_cg_count.release(); d_cg_off.release(); d_scan_tmp.release();
@@ -197,6 +205,7 @@ struct Job {
     const sqg_coord_t *coords = nullptr;  // coordinate batch (bases/base_off unused)
     int64_t meth_draw_base = 0;
     std::string err;  // message of this job's failure (sqg_wait copies it to the context)
+    const sqg_record_info_t *rec = nullptr;   // SQG_WANT_RECORDS
 };
 
 }  // namespace
@@ -642,28 +651,72 @@ int slot_generate(sqg_ctx *ctx, Slot &s, cudaEvent_t before = nullptr, cudaEvent
     return SQG_OK;
 }
 
-// SQG_WANT_SVB: svb-zd streams of the batch's reads, in HBM (sqg_svb.cuh).  One small D2H + sync to size the buffer.
+// SQG_WANT_SVB / SQG_WANT_RECORDS: svb-zd streams or finished BLOW5 records of the batch's reads, in HBM (sqg_svb.cuh).
+// One pass over the signal; the output buffer is sized from an upper bound (3 data bytes per sample), so nothing has to
+// come back to the host before the encoder runs - the total is published behind it.
 int slot_compress(sqg_ctx *ctx, Slot &s) {
     s.svb_bytes = 0;
     if (s.n_reads == 0) return SQG_OK;
     const size_t n = (size_t)s.n_reads;
+    const bool records = (s.want & SQG_WANT_RECORDS) != 0;
+    const sqg_record_info_t *ri = s.rec_info;
+    if (records && (!ri || !ri->read_ids || !ri->id_off)) return fail(ctx, SQG_ERR_ARG, "SQG_WANT_RECORDS needs the reads' ids (sqg_record_info_t)");
+    const size_t nseg_max = (size_t)(s.total_samples / SVB_SEG) + n + 1;
+    int64_t id_bytes = 0;
+    if (records) {
+        id_bytes = ri->id_off[n] - ri->id_off[0];
+        for (size_t r = 0; r < n; r++) {
+            const int64_t l = ri->id_off[r + 1] - ri->id_off[r];
+            if (l < 0 || l > 65535) return fail(ctx, SQG_ERR_ARG, "read id length out of range (uint16, slow5lib)");
+        }
+    }
+    const size_t cap = (size_t)s.total_samples * 3 + (size_t)s.total_samples / 4 + n * (8 + (records ? SVB_REC_HEAD + svb_rec_tail(1) : 0)) +
+                       (size_t)id_bytes + 64;
     CU(s.d_svb_len.ensure(n, false, s.stream));
     CU(s.d_svb_off.ensure(n + 1, false, s.stream));
-    CU(s.h_svb_off.ensure(n + 1));
+    CU(s.d_seg0.ensure(n + 1, false, s.stream));
+    CU(s.d_fixed.ensure(n + 1, false, s.stream));
+    CU(s.d_read_d0.ensure(n, false, s.stream));
+    CU(s.d_seg_state.ensure(nseg_max, false, s.stream));
+    CU(s.d_seg_excl.ensure(nseg_max + 1, false, s.stream));
+    CU(s.d_ticket.ensure(4, false, s.stream));
+    CU(s.d_svb_tot.ensure(4, false, s.stream));
+    CU(s.h_svb_tot.ensure(4));
+    CU(s.d_svb.ensure(cap, false, s.stream));
     SvbParams q;
+    memset(&q, 0, sizeof q);
     q.sig = s.d_sig.p; q.read_sigoff = s.d_sigoff.p; q.read_siglen = s.d_siglen.p;
-    q.svb_len = s.d_svb_len.p; q.svb_off = s.d_svb_off.p; q.svb = nullptr; q.n_reads = (int32_t)s.n_reads;
-    svb_size_kernel<<<(int)s.n_reads, SVB_THREADS, 0, s.stream>>>(q);
-    svb_offsets_kernel<<<1, 1024, 0, s.stream>>>(q);
-    publish_kernel<<<1, 32, 0, s.stream>>>(s.d_svb_off.p + n, 1, nullptr, 0, s.h_svb_off.p + n);
-    ctx->launches += 1;
-    CU(cudaStreamSynchronize(s.stream));
-    s.svb_bytes = s.h_svb_off.p[n];
-    CU(s.d_svb.ensure((size_t)std::max<int64_t>(s.svb_bytes, 16), false, s.stream));
-    q.svb = s.d_svb.p;
-    svb_encode_kernel<<<(int)s.n_reads, SVB_THREADS, 0, s.stream>>>(q);
-    ctx->launches += 3;
+    q.svb_len = s.d_svb_len.p; q.svb_off = s.d_svb_off.p; q.out = s.d_svb.p; q.n_reads = (int32_t)s.n_reads;
+    q.seg0 = s.d_seg0.p; q.fixed = s.d_fixed.p; q.seg_state = s.d_seg_state.p; q.seg_excl = s.d_seg_excl.p;
+    q.read_d0 = s.d_read_d0.p; q.ticket = s.d_ticket.p; q.totals = s.d_svb_tot.p;
+    if (records) {
+        CU(s.d_ids.ensure((size_t)std::max<int64_t>(id_bytes, 1), false, s.stream));
+        CU(s.d_id_off.ensure(n + 1, false, s.stream));
+        CU(cudaMemcpyAsync(s.d_ids.p, ri->read_ids + ri->id_off[0], (size_t)id_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_id_off.p, ri->id_off, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        q.records = 1;
+        q.ids = s.d_ids.p - ri->id_off[0];   // (id_off values are used as they are)
+        q.id_off = s.d_id_off.p;
+        q.read_offset = s.d_offset.p; q.read_median = s.d_median.p;
+        const sqg_profile_t &pr = ctx->cfg.profile;
+        q.digitisation = pr.digitisation; q.range = pr.range; q.sample_rate = pr.sample_rate;
+        q.read_number0 = s.first_read;
+        q.start_time0 = ri->start_time0;
+        q.ont_friendly = ri->ont_friendly ? 1 : 0;
+    }
+    CU(cudaMemsetAsync(s.d_seg_state.p, 0, nseg_max * sizeof(unsigned long long), s.stream));
+    CU(cudaMemsetAsync(s.d_ticket.p, 0, 4 * sizeof(unsigned int), s.stream));
+    CU(cudaMemsetAsync(s.d_read_d0.p, 0xFF, n * sizeof(unsigned long long), s.stream));
+    svb_layout_kernel<<<1, 1024, 0, s.stream>>>(q);
+    svb_encode_kernel<<<ctx->num_sms * 8, SVB_THREADS, 0, s.stream>>>(q);
+    svb_finish_kernel<<<(int)((n + 7) / 8), 256, 0, s.stream>>>(q);
+    if (records) svb_start_time_kernel<<<1, 1024, 0, s.stream>>>(q);
+    publish_kernel<<<1, 32, 0, s.stream>>>(s.d_svb_tot.p, 1, nullptr, 0, s.h_svb_tot.p);
+    ctx->launches += records ? 5 : 4;
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.stream));
+    s.svb_bytes = s.h_svb_tot.p[0];
+    if (s.svb_bytes < 0 || (size_t)s.svb_bytes > cap) return fail(ctx, SQG_ERR_CUDA, "svb-zd encoder: output beyond its bound");
     return SQG_OK;
 }
 
@@ -697,7 +750,7 @@ int slot_sstext(sqg_ctx *ctx, Slot &s) {
 }
 
 void fill_result(Slot &s, sqg_result_t *res) {
-    const bool svb = (s.want & SQG_WANT_SVB) != 0;
+    const bool svb = (s.want & (SQG_WANT_SVB | SQG_WANT_RECORDS)) != 0;
     const bool want_bases = s.from_coords && (s.want & SQG_WANT_BASES);
     res->n_reads = s.n_reads;
     res->total_samples = s.total_samples;
@@ -721,7 +774,7 @@ void fill_result(Slot &s, sqg_result_t *res) {
 // D2H of everything the caller gets back; fills *res.  Synchronises the slot's stream.
 int slot_fetch(sqg_ctx *ctx, Slot &s, sqg_result_t *res) {
     const size_t n = (size_t)s.n_reads;
-    const bool svb = (s.want & SQG_WANT_SVB) != 0;
+    const bool svb = (s.want & (SQG_WANT_SVB | SQG_WANT_RECORDS)) != 0;
     if (svb) {
         CU(s.h_svb_len.ensure(n + 1));
         CU(s.h_svb_off.ensure(n + 1));
@@ -781,9 +834,9 @@ int slot_run_all(sqg_ctx *ctx, Slot &s, int64_t n_reads, const char *bases, cons
         NvtxRange r("sqg:generate (signal kernel)");
         if ((rc = slot_generate(ctx, s)) != SQG_OK) return rc;
     }
-    if (want & (SQG_WANT_SVB | SQG_WANT_SS_TEXT)) {
-        NvtxRange r("sqg:compress (svb-zd, ss text)");
-        if ((want & SQG_WANT_SVB) && (rc = slot_compress(ctx, s)) != SQG_OK) return rc;
+    if (want & (SQG_WANT_SVB | SQG_WANT_RECORDS | SQG_WANT_SS_TEXT)) {
+        NvtxRange r("sqg:compress (svb-zd / records, ss text)");
+        if ((want & (SQG_WANT_SVB | SQG_WANT_RECORDS)) && (rc = slot_compress(ctx, s)) != SQG_OK) return rc;
         if ((want & SQG_WANT_SS_TEXT) && (rc = slot_sstext(ctx, s)) != SQG_OK) return rc;
     }
     NvtxRange r("sqg:fetch (D2H)");
@@ -802,6 +855,7 @@ void worker_main(sqg_ctx *ctx, int slot_idx) {
             ctx->queues[slot_idx].pop_front();
         }
         tl_err_sink = &job->err;   // (this thread's CU()/fail() messages belong to the job)
+        ctx->slots[slot_idx].rec_info = job->rec;
         int rc = slot_run_all(ctx, ctx->slots[slot_idx], job->n_reads, job->bases, job->base_off, job->first_read,
                               job->want, nullptr, job->coords, job->meth_draw_base);
         tl_err_sink = nullptr;
@@ -1103,7 +1157,7 @@ int sqg_gen_batch(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int6
 
 static int submit_job(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
                       const sqg_coord_t *coords, int64_t meth_draw_base, int64_t first_read_index, uint32_t want,
-                      sqg_ticket_t *ticket) {
+                      sqg_ticket_t *ticket, const sqg_record_info_t *rec = nullptr) {
     if (!ctx || !ticket) return SQG_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_dispatcher(ctx);
@@ -1116,6 +1170,7 @@ static int submit_job(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const 
         return false;
     });
     Job *job = new Job{ctx->next_ticket++, slot, n_reads, bases, base_off, first_read_index, want, 1, coords, meth_draw_base};
+    job->rec = rec;
     ctx->slot_busy[slot] = 1;
     ctx->jobs[job->ticket] = job;
     ctx->queues[slot].push_back(job);
@@ -1128,6 +1183,23 @@ static int submit_job(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const 
 int sqg_submit(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
                int64_t first_read_index, uint32_t want, sqg_ticket_t *ticket) {
     return submit_job(ctx, n_reads, bases, base_off, nullptr, 0, first_read_index, want, ticket);
+}
+
+int sqg_gen_batch_records(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                          int64_t first_read_index, const sqg_record_info_t *rec, uint32_t want, sqg_result_t *res) {
+    if (!ctx || !res) return SQG_ERR_ARG;
+    if (n_reads > 0 && !rec) return fail(ctx, SQG_ERR_ARG, "null record info");
+    CU(cudaSetDevice(ctx->device));
+    ctx->sync_slot.rec_info = rec;
+    const int rc = slot_run_all(ctx, ctx->sync_slot, n_reads, bases, base_off, first_read_index, want | SQG_WANT_RECORDS, res);
+    ctx->sync_slot.rec_info = nullptr;
+    return rc;
+}
+
+int sqg_submit_records(sqg_ctx_t *ctx, int64_t n_reads, const char *bases, const int64_t *base_off,
+                       int64_t first_read_index, const sqg_record_info_t *rec, uint32_t want, sqg_ticket_t *ticket) {
+    if (n_reads > 0 && !rec) return ctx ? fail(ctx, SQG_ERR_ARG, "null record info") : SQG_ERR_ARG;
+    return submit_job(ctx, n_reads, bases, base_off, nullptr, 0, first_read_index, want | SQG_WANT_RECORDS, ticket, rec);
 }
 
 int sqg_submit_coords(sqg_ctx_t *ctx, int64_t n_reads, const sqg_coord_t *coords, int64_t first_read_index,
@@ -1306,7 +1378,7 @@ int sqg_dev_batch_fetch(sqg_ctx_t *ctx, sqg_dev_batch_t *b, sqg_result_t *res) {
     if (!ctx || !b || !res) return SQG_ERR_ARG;
     if (!b->planned) return fail(ctx, SQG_ERR_STATE, "batch has not been run");
     CU(cudaSetDevice(ctx->device));
-    if (b->slot.want & SQG_WANT_SVB) {
+    if (b->slot.want & (SQG_WANT_SVB | SQG_WANT_RECORDS)) {
         int rc = slot_compress(ctx, b->slot);
         if (rc != SQG_OK) return rc;
     }
