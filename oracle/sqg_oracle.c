@@ -429,7 +429,7 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                  * Cq = 96 u + 32 g + l uses blocks A = 64 u + 2 l and B = A + 1:
                  *   g = 0: sample e -> word e/2 of A, F0 (e even) / F1 (e odd);   g = 2: the same of B;
                  *   g = 1: F2 of word e of A (e < 4) or of word e - 4 of B.
-                 * The draw's table class is l XOR five hash bits of (Cq >> 5, read): a bijection of the 32 chunks of a
+                 * The draw's table class is l XOR five hash bits of (unit, group, read): a bijection of the 32 chunks of a
                  * group, different from group to group, so no sample position is tied to one class. */
                 uint32_t q = (uint32_t)(rna ? total - 1 - n : n);
                 uint32_t Cq = q >> 3, e = q & 7;
@@ -445,9 +445,9 @@ int64_t sqo_gen_sig(void *hv, const char *read, int32_t len, int64_t read_index,
                     uint32_t x = w[e >> 1];
                     d10 = (e & 1) ? (x >> 17) & 0x3FFu : (x >> 7) & 0x3FFu;
                 }
-                uint32_t h = (Cq >> 5) * 0x9E3779B1u + r_lo * 0x85EBCA6Bu; /* one xorshift-multiply round, top five bits */
+                uint32_t h = u * 0x9E3779B1u + r_lo * 0x85EBCA6Bu; /* one xorshift-multiply round per unit and read ... */
                 h ^= h >> 15;
-                h = (h * 0x2C1B3C6Du) >> 27;
+                h = ((h * 0x2C1B3C6Du) >> (27 - 5 * g)) & 31u;           /* ... group g takes bits 27-5g .. 31-5g */
                 float z = sqo_z32(o->zt, (d10 << 5) | (l ^ h), o->key, q, r_lo, r_hi, ST_AMP_TAIL);
                 raw[n] = to_i16_f(fma_rz(z, A, Bq));
             }

@@ -123,14 +123,21 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t off) {
 //   g = 0: word e/2 of A, field F0 (e even) or F1 (e odd)        g = 2: the same of B
 //   g = 1: field F2 of word e of A (e < 4) or of word e - 4 of B (e >= 4)
 // A lane of the signal kernel handles the three chunks l, 32 + l, 64 + l of a unit with two Philox calls.  The draw's
-// table CLASS is l ^ h, h = five hash bits (amp_mix) of the chunk's group of 32 (and of the read): within a group the classes are a
-// bijection of the lanes - one bank per lane - and over the groups every position of the signal meets every class.
-__device__ __forceinline__ uint32_t amp_mix(uint32_t x) {   // x = group * 0x9E3779B1 + amp_hmul(read): one xorshift-multiply round
+// table CLASS is l ^ h, h = five bits of ONE hash per unit and read (amp_mix; group g of the unit takes bits 27-5g .. 31-5g):
+// within a group the classes are a bijection of the lanes - one bank per lane - and over the units every position of the
+// signal meets every class.
+__device__ __forceinline__ uint32_t amp_mix(uint32_t x) {   // x = unit * 0x9E3779B1 + amp_hmul(read): one xorshift-multiply round
     x ^= x >> 15;
-    return (x * 0x2C1B3C6Du) >> 27;
+    return x * 0x2C1B3C6Du;
 }
-__device__ __forceinline__ uint32_t amp_class_hash(uint32_t group, uint32_t hmul) { return amp_mix(group * 0x9E3779B1u + hmul); }
-__device__ __forceinline__ uint32_t amp_class4(uint32_t Cq, uint32_t hmul) { return ((Cq & 31u) ^ amp_class_hash(Cq >> 5, hmul)) << 2; }
+// (h << 2) of group g (0..2) of a unit whose hash is x
+template <int G>
+__device__ __forceinline__ uint32_t amp_h4(uint32_t x) { return (x >> (25 - 5 * G)) & 0x7Cu; }
+__device__ __forceinline__ uint32_t amp_h4(uint32_t x, uint32_t g) { return (x >> (25u - 5u * g)) & 0x7Cu; }
+__device__ __forceinline__ uint32_t amp_class4(uint32_t Cq, uint32_t hmul) {   // any chunk, by itself
+    const uint32_t u = Cq / UNIT_C, r = Cq - u * UNIT_C;
+    return ((r & 31u) << 2) ^ amp_h4(amp_mix(u * 0x9E3779B1u + hmul), r >> 5);
+}
 __device__ __forceinline__ uint32_t amp_hmul(uint32_t r_lo) { return r_lo * 0x85EBCA6Bu; }
 // a field moved to bits 7..16, where z_offset() masks it: F1 by a multiply-high (x >> 10 on the FMA pipe, which has
 // room; the ALU pipe does not), F2 by a rotation
@@ -346,10 +353,7 @@ __device__ __forceinline__ uint32_t group_chunk(const GenParams &p, const unsign
     } else {
         chunk_kmers<false>(p, smem, map_off, t.fmap, t.fix_f0, c, k0, m1);
     }
-    // the emitted group of the chunk (the same for all lanes: groups are aligned in the emitted signal), computed from
-    // warp-uniform values so that the hash stays off the vector pipes
-    const uint32_t Gq = REV ? (t.C0 >> 5) - g : (t.C0 >> 5) + g;
-    const uint32_t class4 = lc.lane4 ^ (amp_class_hash(Gq, t.hmul) << 2);
+    const uint32_t class4 = amp_class4(Cq, t.hmul);   // (= lane4 ^ the group's five hash bits: groups are aligned in the emitted signal)
     return fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, false, false, pk);
 }
 
@@ -386,6 +390,7 @@ __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigne
     }
     uint32_t bad[3];
     uint4 pk[3];
+    const uint32_t hx = amp_mix(H);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         uint32_t k0, m1, dw[8];
@@ -399,10 +404,13 @@ __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigne
         if (i == 0) amp_fields<REV ? 2 : 0>(A, B, dw);
         else if (i == 1) amp_fields<1>(A, B, dw);
         else amp_fields<REV ? 0 : 2>(A, B, dw);
-        const uint32_t Hi = REV ? H - (uint32_t)i * 0x9E3779B1u : H + (uint32_t)i * 0x9E3779B1u;   // (warp-uniform)
-        const uint32_t class4 = lc.lane4 ^ (amp_mix(Hi) << 2);
+        const uint32_t class4 = lc.lane4 ^ (i == 0 ? amp_h4<REV ? 2 : 0>(hx) : i == 1 ? amp_h4<1>(hx) : amp_h4<REV ? 0 : 2>(hx));
         bad[i] = fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, p.l2_vote != 0, true, pk[i]);
+#ifdef SQG_STORE_EARLY
+        st_cs_v4(REV ? dst - 256 * i : dst + 256 * i, pk[i]);
+#endif
     }
+#ifndef SQG_STORE_EARLY
 #pragma unroll
     for (int i = 0; i < 3; i++) {
 #ifdef SQG_KO_STORE
@@ -410,6 +418,7 @@ __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigne
 #endif
         st_cs_v4(REV ? dst - 256 * i : dst + 256 * i, pk[i]);
     }
+#endif
     if (__builtin_expect((bad[0] | bad[1] | bad[2]) != 0, 0)) {
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -440,13 +449,13 @@ __device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned ch
                 int16_t *dst = t.out + (size_t)Cq0 * 8;
                 const uint32_t u0 = REV ? (t.C0 / UNIT_C) - uf : (t.C0 / UNIT_C) + uf;   // emitted unit (frame units are aligned with them)
                 uint32_t blk = 64u * u0 + 2u * (uint32_t)lane;
-                uint32_t H = (REV ? 3 * u0 + 2 : 3 * u0) * 0x9E3779B1u + t.hmul;
+                uint32_t H = u0 * 0x9E3779B1u + t.hmul;
                 for (; uf < u_end; uf++) {
                     emit_unit_fast<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, uf, ent_addr, dst, blk, H);
                     ent_addr += 3 * 64;
                     dst = REV ? dst - 768 : dst + 768;
                     blk = REV ? blk - 64 : blk + 64;
-                    H = REV ? H - 3u * 0x9E3779B1u : H + 3u * 0x9E3779B1u;
+                    H = REV ? H - 0x9E3779B1u : H + 0x9E3779B1u;
                 }
                 t.cur_c = UNIT_C * u_end;
                 continue;

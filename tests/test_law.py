@@ -4,7 +4,7 @@ fourth moment and tail counts - from the reference's own rand.h path (src/rand.h
 
 A draw = 10 random bits (sign + 9-bit slot) and a CLASS in 0..31; within a class the 1024 values are equiprobable atoms
 (conditional RMS of 512 half-normal cells, scaled to unit variance; the outermost cell of class 0 is refined by 13 more
-bits).  The class of the sample at emitted position q is  (chunk & 31) XOR hash(chunk >> 5, read)  with chunk = q >> 3:
+bits).  The class of the sample at emitted position q is  (chunk & 31) XOR hash(unit, group, read)  with chunk = q >> 3 (a unit = 3 groups of 32 chunks):
 inside a group of 32 chunks every class occurs once (one shared-memory bank per lane), across groups a position meets
 all 32 classes, so the law of a sample at ANY position is the pooled law: 32768 atoms, |z| up to 5.91.
 """
@@ -56,9 +56,10 @@ def test_per_class_and_pooled_law_from_the_table():
 def amp_class(q, r_lo):
     """class of the sample at emitted position q of read r_lo (oracle/sqg_oracle.c, sqg_signal.cuh amp_class4)"""
     cq = q >> 3
-    x = (((cq >> 5) * 0x9E3779B1) + ((r_lo * 0x85EBCA6B) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    u, g = cq // 96, (cq % 96) >> 5
+    x = ((u * 0x9E3779B1) + ((r_lo * 0x85EBCA6B) & 0xFFFFFFFF)) & 0xFFFFFFFF
     x ^= x >> 15
-    h = ((x * 0x2C1B3C6D) & 0xFFFFFFFF) >> 27
+    h = (((x * 0x2C1B3C6D) & 0xFFFFFFFF) >> (27 - 5 * g)) & 31
     return (cq & 31) ^ h
 
 
