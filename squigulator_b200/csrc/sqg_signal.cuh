@@ -146,7 +146,16 @@ __device__ __forceinline__ uint32_t amp_f1(uint32_t x) {
     asm("mul.hi.u32 %0, %1, 4194304;" : "=r"(r) : "r"(x));
     return r;
 }
+#ifdef SQG_F2_IMAD
+__device__ __forceinline__ uint32_t amp_f2(uint32_t x) {   // the rotation as two multiplies: (x << 12) + (x >> 20), on the FMA pipe
+    uint32_t hi, r;
+    asm("mul.hi.u32 %0, %1, 4096;" : "=r"(hi) : "r"(x));
+    asm("mad.lo.u32 %0, %1, 4096, %2;" : "=r"(r) : "r"(x), "r"(hi));
+    return r;
+}
+#else
 __device__ __forceinline__ uint32_t amp_f2(uint32_t x) { return __funnelshift_r(x, x, 20); }
+#endif
 template <int G>
 __device__ __forceinline__ void amp_fields(const uint4 &A, const uint4 &B, uint32_t (&dw)[8]) {
     const uint32_t a[4] = {A.x, A.y, A.z, A.w}, b[4] = {B.x, B.y, B.z, B.w};
@@ -380,7 +389,7 @@ __device__ __forceinline__ void emit_group_single(const GenParams &p, const unsi
 // One whole unit: frame groups 3 uf .. 3 uf + 2.  Three independent chunks per lane from two Philox blocks, one check for
 // the rare redo behind them.  ent_addr / dst / blk / H walk from unit to unit in the caller: the lane's map entry of the
 // unit's first group, where its first chunk goes, its first Philox block, the class hash's argument of the first group.
-template <bool NOISY, bool RAND_DWELL, bool REV>
+template <bool NOISY, bool RAND_DWELL, bool REV, bool L2V>
 __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigned char *smem, const Run &t, const LaneC &lc, uint32_t map_off,
                                                uint32_t uf, uint32_t ent_addr, int16_t *dst, uint32_t blk, uint32_t H) {
     uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
@@ -405,7 +414,7 @@ __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigne
         else if (i == 1) amp_fields<1>(A, B, dw);
         else amp_fields<REV ? 0 : 2>(A, B, dw);
         const uint32_t class4 = lc.lane4 ^ (i == 0 ? amp_h4<REV ? 2 : 0>(hx) : i == 1 ? amp_h4<1>(hx) : amp_h4<REV ? 0 : 2>(hx));
-        bad[i] = fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, p.l2_vote != 0, true, pk[i]);
+        bad[i] = fast_chunk<NOISY, REV>(k0, m1, map_off + W_PAR, dw, class4, t.c_r, L2V, true, pk[i]);
 #ifdef SQG_STORE_EARLY
         st_cs_v4(REV ? dst - 256 * i : dst + 256 * i, pk[i]);
 #endif
@@ -450,12 +459,24 @@ __device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned ch
                 const uint32_t u0 = REV ? (t.C0 / UNIT_C) - uf : (t.C0 / UNIT_C) + uf;   // emitted unit (frame units are aligned with them)
                 uint32_t blk = 64u * u0 + 2u * (uint32_t)lane;
                 uint32_t H = u0 * 0x9E3779B1u + t.hmul;
-                for (; uf < u_end; uf++) {
-                    emit_unit_fast<NOISY, RAND_DWELL, REV>(p, smem, t, lc, map_off, uf, ent_addr, dst, blk, H);
-                    ent_addr += 3 * 64;
-                    dst = REV ? dst - 768 : dst + 768;
-                    blk = REV ? blk - 64 : blk + 64;
-                    H = REV ? H - 0x9E3779B1u : H + 0x9E3779B1u;
+                // (two copies of the loop: whether a chunk's third k-mer level is voted on is a per-profile constant, and a
+                //  test of it inside the loop costs seven issue slots per unit)
+                if (p.l2_vote) {
+                    for (; uf < u_end; uf++) {
+                        emit_unit_fast<NOISY, RAND_DWELL, REV, true>(p, smem, t, lc, map_off, uf, ent_addr, dst, blk, H);
+                        ent_addr += 3 * 64;
+                        dst = REV ? dst - 768 : dst + 768;
+                        blk = REV ? blk - 64 : blk + 64;
+                        H = REV ? H - 0x9E3779B1u : H + 0x9E3779B1u;
+                    }
+                } else {
+                    for (; uf < u_end; uf++) {
+                        emit_unit_fast<NOISY, RAND_DWELL, REV, false>(p, smem, t, lc, map_off, uf, ent_addr, dst, blk, H);
+                        ent_addr += 3 * 64;
+                        dst = REV ? dst - 768 : dst + 768;
+                        blk = REV ? blk - 64 : blk + 64;
+                        H = REV ? H - 0x9E3779B1u : H + 0x9E3779B1u;
+                    }
                 }
                 t.cur_c = UNIT_C * u_end;
                 continue;
