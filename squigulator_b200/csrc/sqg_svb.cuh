@@ -191,22 +191,32 @@ __global__ void __launch_bounds__(SVB_THREADS) svb_encode_kernel(const SvbParams
         uint32_t mine_all = 0;
         {
             int32_t prev = (w_i0 && w_i0 < n) ? (int32_t)x[w_i0 - 1] : 0;
-#pragma unroll 2
-            for (int st = 0; st < SVB_WSTEPS; st++) {
-                const uint32_t i0 = w_i0 + st * 256 + lane * 8;
-                if (w_i0 + st * 256 >= n) break;
-                uint4 q = make_uint4(0, 0, 0, 0);
-                if (i0 < n) q = *reinterpret_cast<const uint4 *>(x + i0);
-                int32_t pl = __shfl_up_sync(0xffffffffu, svb_last(q), 1);
-                if (lane == 0) pl = prev;
-                prev = __shfl_sync(0xffffffffu, svb_last(q), 31);
-                uint32_t v[8], nb[8];
-                svb_code8(q, pl, v, nb);
-                if (i0 + 8 <= n) {
-                    mine_all += ((nb[0] + nb[1]) + (nb[2] + nb[3])) + ((nb[4] + nb[5]) + (nb[6] + nb[7]));
-                } else {
+            // four steps at a time, their loads issued together: the sweep is bound by the bytes in flight
+            for (int st0 = 0; st0 < SVB_WSTEPS; st0 += 4) {
+                if (w_i0 + st0 * 256 >= n) break;
+                uint4 qq[4];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) mine_all += (i0 + j < n) ? nb[j] : 0u;
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i0 = w_i0 + (st0 + u) * 256 + lane * 8;
+                    qq[u] = make_uint4(0, 0, 0, 0);
+                    if (i0 < n) qq[u] = *reinterpret_cast<const uint4 *>(x + i0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i0 = w_i0 + (st0 + u) * 256 + lane * 8;
+                    if (w_i0 + (st0 + u) * 256 >= n) break;
+                    const uint4 q = qq[u];
+                    int32_t pl = __shfl_up_sync(0xffffffffu, svb_last(q), 1);
+                    if (lane == 0) pl = prev;
+                    prev = __shfl_sync(0xffffffffu, svb_last(q), 31);
+                    uint32_t v[8], nb[8];
+                    svb_code8(q, pl, v, nb);
+                    if (i0 + 8 <= n) {
+                        mine_all += ((nb[0] + nb[1]) + (nb[2] + nb[3])) + ((nb[4] + nb[5]) + (nb[6] + nb[7]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) mine_all += (i0 + j < n) ? nb[j] : 0u;
+                    }
                 }
             }
         }
@@ -288,12 +298,15 @@ __global__ void __launch_bounds__(SVB_THREADS) svb_encode_kernel(const SvbParams
         uint8_t *stage = s_stage[warp];
         // ---- second sweep: the warp codes its chunk, 256 samples at a time, through its own staging area; no CTA barrier ----
         int32_t prev = w_i0 ? (int32_t)x[w_i0 - 1] : 0;
+        uint4 qn = make_uint4(0, 0, 0, 0);
+        if (w_i0 + lane * 8 < n) qn = *reinterpret_cast<const uint4 *>(x + w_i0 + lane * 8);
         for (int st = 0; st < SVB_WSTEPS; st++) {
             const uint32_t step_i0 = w_i0 + st * 256;
             if (step_i0 >= n) break;
             const uint32_t i0 = step_i0 + lane * 8;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (i0 < n) q = *reinterpret_cast<const uint4 *>(x + i0);
+            const uint4 q = qn;
+            qn = make_uint4(0, 0, 0, 0);
+            if (st + 1 < SVB_WSTEPS && i0 + 256 < n) qn = *reinterpret_cast<const uint4 *>(x + i0 + 256);
             int32_t pl = __shfl_up_sync(0xffffffffu, svb_last(q), 1);
             if (lane == 0) pl = prev;
             prev = __shfl_sync(0xffffffffu, svb_last(q), 31);
