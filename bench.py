@@ -511,6 +511,16 @@ def main():
         g3.close()
         extra["legacy-rng dna-r9-prom"] = {"config": "configs[1] profile, SQG_RNG_LEGACY, host buffers in and out (one synchronous batch of 512 reads)",
                                            "value": sum(len(r["sig"]) for r in rr) / dt, "unit": "samples/s per GPU"}
+        # the per-read seam: sqg_gen_sig(), the call with gen_sig()'s own shape (src/gensig.c:346) for a host that cannot
+        # batch - one read per call, planning + signal kernels + copies + a malloc'd result each time
+        g4, _k4 = make_gen(wl)
+        g4.gen_sig(reads[0], read_index=0)
+        t0 = time.perf_counter()
+        ns = sum(len(g4.gen_sig(r, read_index=i)["sig"]) for i, r in enumerate(reads[:128]))
+        dt = time.perf_counter() - t0
+        g4.close()
+        extra["per-read seam sqg_gen_sig"] = {"config": f"{wl['config']} profile, one synchronous call per read (128 reads of ~{args.read_len} nt)",
+                                              "value": ns / dt, "unit": "samples/s per GPU", "calls_per_s": 128 / dt}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_extra:
