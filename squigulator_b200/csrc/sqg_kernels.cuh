@@ -385,17 +385,24 @@ __global__ void __launch_bounds__(1024) read_offsets_kernel(const __grid_constan
     __shared__ uint64_t s_raw[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint64_t carry = 0, raw_total = 0;
+    // the lengths of round i+1 are requested before round i is scanned (the kernel is one CTA: nothing else hides the latency)
+    auto load4 = [&](int r) -> uint4 {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r + 3 < p.n_reads) {
+            v = *reinterpret_cast<const uint4 *>(p.read_siglen + r);   // (cudaMalloc'd, r a multiple of 4)
+        } else {
+            if (r < p.n_reads) v.x = p.read_siglen[r];
+            if (r + 1 < p.n_reads) v.y = p.read_siglen[r + 1];
+            if (r + 2 < p.n_reads) v.z = p.read_siglen[r + 2];
+        }
+        return v;
+    };
+    uint4 vn = load4(4 * tid);
     for (int r0 = 0; r0 < p.n_reads; r0 += 4096) {
         const int r = r0 + 4 * tid;
-        uint32_t l[4] = {0, 0, 0, 0};
-        if (r + 3 < p.n_reads) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p.read_siglen + r);   // (cudaMalloc'd, r a multiple of 4)
-            l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (r + i < p.n_reads) l[i] = p.read_siglen[r + i];
-        }
+        const uint4 vc = vn;
+        vn = load4(r + 4096);
+        const uint32_t l[4] = {vc.x, vc.y, vc.z, vc.w};
         uint64_t al[4], mine = 0, raw = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
