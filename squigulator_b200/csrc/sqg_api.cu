@@ -1157,6 +1157,7 @@ void sqg_destroy(sqg_ctx_t *ctx) {
     ctx->sync_slot.release();
     ctx->d_model.release();
     ctx->d_model_am.release();
+    if (ctx->d_pair_model.p) cudaCtxResetPersistingL2Cache();   // (slot_pin_model: the table's lines go back to the normal policy)
     ctx->d_pair_model.release();
     ctx->d_z.release();
     ctx->d_cnt_kmer.release();

@@ -428,7 +428,11 @@ __device__ __forceinline__ void emit_unit_fast(const GenParams &p, const unsigne
         st_cs_v4(REV ? dst - 256 * i : dst + 256 * i, pk[i]);
     }
 #endif
+#ifdef SQG_KO_EXACT
+    if (pk[0].x == 0x12345678u && pk[1].y == 0x9abcdef0u && (bad[0] | bad[1] | bad[2]) != 0) {
+#else
     if (__builtin_expect((bad[0] | bad[1] | bad[2]) != 0, 0)) {
+#endif
 #pragma unroll
         for (int i = 0; i < 3; i++)
             if (bad[i])
