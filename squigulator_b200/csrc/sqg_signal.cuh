@@ -173,8 +173,11 @@ __device__ __forceinline__ void amp_draws(const GenParams &p, uint32_t Cq, uint3
     const uint32_t u = Cq / UNIT_C, r = Cq - u * UNIT_C, g = r >> 5;
     const uint32_t blk = 64u * u + 2u * (r & 31u);
     uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
-    if (g != 2) A = philox4x32_rk(blk, r_lo, r_hi, ST_AMP, p.rk);
-    if (g != 0) B = philox4x32_rk(blk + 1, r_lo, r_hi, ST_AMP, p.rk);
+    // (the key schedule by additions, not from p.rk: in the out-of-line callers `p` is a generic pointer to the kernel's
+    //  parameter block, and fourteen generic loads per block would sit on the critical path of a one-lane redo)
+    const uint32_t k0 = p.key0, k1 = p.key1;
+    if (g != 2) A = philox4x32(blk, r_lo, r_hi, ST_AMP, k0, k1);
+    if (g != 0) B = philox4x32(blk + 1, r_lo, r_hi, ST_AMP, k0, k1);
     if (g == 0) amp_fields<0>(A, B, dw);
     else if (g == 1) amp_fields<1>(A, B, dw);
     else amp_fields<2>(A, B, dw);
