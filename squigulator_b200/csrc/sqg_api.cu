@@ -128,6 +128,7 @@ struct Slot {
     DevBuf<uint8_t> d_svb;
     DevBuf<int64_t> d_seg0, d_fixed, d_svb_tot, d_id_off;
     DevBuf<unsigned long long> d_seg_state, d_seg_excl, d_read_d0;
+    DevBuf<int32_t> d_seg_read;
     DevBuf<unsigned int> d_ticket;
     DevBuf<char> d_ids;
     PinBuf<int64_t> h_svb_tot;
@@ -178,7 +179,7 @@ struct Slot {
         h_ss_off.release(); h_siglen.release(); h_offset.release(); h_median.release(); h_sig.release();
         h_ss.release();
         d_svb_len.release(); d_svb_off.release(); d_svb.release(); h_svb_len.release(); h_svb_off.release(); h_svb.release();
-        d_seg0.release(); d_fixed.release(); d_svb_tot.release(); d_id_off.release(); d_seg_state.release(); d_seg_excl.release();
+        d_seg0.release(); d_fixed.release(); d_svb_tot.release(); d_id_off.release(); d_seg_state.release(); d_seg_excl.release(); d_seg_read.release();
         d_read_d0.release(); d_ticket.release(); d_ids.release(); h_svb_tot.release();
         d_sst_len.release(); d_sst_off.release(); d_ss_off.release(); d_sst.release(); h_sst_off.release(); h_sst.release();
         d_pieces.release(); h_pieces.release();
@@ -709,6 +710,7 @@ int slot_compress(sqg_ctx *ctx, Slot &s) {
     CU(s.d_fixed.ensure(n + 1, false, s.stream));
     CU(s.d_read_d0.ensure(n, false, s.stream));
     CU(s.d_seg_state.ensure(nseg_max, false, s.stream));
+    CU(s.d_seg_read.ensure(nseg_max * 8, false, s.stream));   // (32-byte records)
     CU(s.d_seg_excl.ensure(nseg_max + 1, false, s.stream));
     CU(s.d_ticket.ensure(4, false, s.stream));
     CU(s.d_svb_tot.ensure(4, false, s.stream));
@@ -719,7 +721,7 @@ int slot_compress(sqg_ctx *ctx, Slot &s) {
     q.sig = s.d_sig.p; q.read_sigoff = s.d_sigoff.p; q.read_siglen = s.d_siglen.p;
     q.svb_len = s.d_svb_len.p; q.svb_off = s.d_svb_off.p; q.out = s.d_svb.p; q.n_reads = (int32_t)s.n_reads;
     q.seg0 = s.d_seg0.p; q.fixed = s.d_fixed.p; q.seg_state = s.d_seg_state.p; q.seg_excl = s.d_seg_excl.p;
-    q.read_d0 = s.d_read_d0.p; q.ticket = s.d_ticket.p; q.totals = s.d_svb_tot.p;
+    q.read_d0 = s.d_read_d0.p; q.ticket = s.d_ticket.p; q.totals = s.d_svb_tot.p; q.seg_read = s.d_seg_read.p;
     if (records) {
         CU(s.d_ids.ensure((size_t)std::max<int64_t>(id_bytes, 1), false, s.stream));
         CU(s.d_id_off.ensure(n + 1, false, s.stream));
@@ -739,11 +741,12 @@ int slot_compress(sqg_ctx *ctx, Slot &s) {
     CU(cudaMemsetAsync(s.d_ticket.p, 0, 4 * sizeof(unsigned int), s.stream));
     CU(cudaMemsetAsync(s.d_read_d0.p, 0xFF, n * sizeof(unsigned long long), s.stream));
     svb_layout_kernel<<<1, 1024, 0, s.stream>>>(q);
+    svb_segmap_kernel<<<(int)((n + 7) / 8), 256, 0, s.stream>>>(q);
     svb_encode_kernel<<<ctx->num_sms * 8, SVB_THREADS, 0, s.stream>>>(q);
     svb_finish_kernel<<<(int)((n + 7) / 8), 256, 0, s.stream>>>(q);
     if (records) svb_start_time_kernel<<<1, 1024, 0, s.stream>>>(q);
     publish_kernel<<<1, 32, 0, s.stream>>>(s.d_svb_tot.p, 1, nullptr, 0, s.h_svb_tot.p);
-    ctx->launches += records ? 5 : 4;
+    ctx->launches += records ? 6 : 5;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s.stream));
     s.svb_bytes = s.h_svb_tot.p[0];

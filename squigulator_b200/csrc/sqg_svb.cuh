@@ -8,17 +8,19 @@
 // signal compression SVB_ZD - record size, read id, primary fields, stream, auxiliary fields - all records back to back,
 // so that the host's part of writing them is one fwrite.
 //
-// ONE pass over the signal in HBM.  The reads are cut into SEGMENTS of 32768 samples; a CTA takes segments in ticket order
-// (atomic counter, so that a segment's predecessors are always running or done), sizes it (first sweep), learns where its
-// data bytes go from a decoupled look-back over the segments before it (status | value words, as in single-pass prefix
-// scans; the whole CTA inspects 256 predecessors at a time - the speed of that frontier is what bounds a single-pass
-// encoder with small work items), then codes it strip by strip through shared memory (second sweep: the segment's 64 KB
-// come from L2).  What does not depend on the data - record header, keys, auxiliary fields - has a position
-// known up front (L1), so:   byte position of a segment's data = fixed[read] + (data bytes of ALL segments before it).
+// ONE pass over the signal, every sample coded ONCE.  The reads are cut into SEGMENTS of 8192 samples; a CTA takes
+// segments in ticket order (atomic counter, so that a segment's predecessors are always running or done), codes the segment
+// into shared memory (each warp its own 1024 samples: keys and data bytes, a running offset from a warp scan per 256
+// samples), learns where its data bytes go from a decoupled look-back over the segments before it (status | value words,
+// as in single-pass prefix scans; the whole CTA inspects 256 predecessors at a time), and copies keys and data out with
+// 16-byte stores (the staging area is read through a byte-funnel, so that the stores are aligned whatever the position).
+// What does not depend on the data - record header, keys, auxiliary fields - has a position known up front (L1), so:
+//   byte position of a segment's data = fixed[read] + (data bytes of ALL segments before it).
 //
 //   L1 svb_layout_kernel  one CTA : per read - segments, fixed bytes before its data; scans              -> seg0, fixed
-//   L2 svb_encode_kernel  persistent-by-ticket: keys + data of every segment, staged in shared memory and copied out
-//                         with 16-byte stores; per segment the data bytes before it                      -> out, seg_excl
+//      svb_segmap_kernel  warp per read: which read a segment belongs to                                 -> seg_read
+//   L2 svb_encode_kernel  persistent-by-ticket: keys + data of every segment; per segment the data bytes before it
+//                                                                                                         -> out, seg_excl
 //   L3 svb_finish_kernel  warp per read: stream header / record header and auxiliary fields, offsets     -> out, off, len
 #pragma once
 #include <cstdint>
@@ -36,6 +38,7 @@ struct SvbParams {
     int32_t n_reads;
     // layout (L1)
     int64_t *seg0;               // n_reads + 1: first segment of read r; [n_reads] = number of segments
+    int32_t *seg_read;           // per segment a 32-byte record: {read, samples of the read, segment within the read, -, arena offset of the read (8 bytes), -, -} (svb_segmap_kernel)
     int64_t *fixed;              // n_reads + 1: bytes that do not depend on the data, up to the start of read r's data area
     unsigned long long *seg_state;   // per segment: look-back word (zeroed before L2)
     unsigned long long *seg_excl;    // per segment (+1): data bytes of all segments before it; [segments] = all data bytes
@@ -54,9 +57,11 @@ struct SvbParams {
 };
 
 constexpr int SVB_THREADS = 256;
-constexpr int SVB_STRIP = SVB_THREADS * 8;        // samples per strip: 8 consecutive samples per thread
-constexpr int SVB_STRIPS = 16;
-constexpr int SVB_SEG = SVB_STRIP * SVB_STRIPS;   // samples per segment (one look-back per segment)
+constexpr int SVB_WARPS = SVB_THREADS / 32;
+constexpr int SVB_WCHUNK = 1024;                  // samples of a segment coded by one warp: 4 steps of 256 (8 per lane)
+constexpr int SVB_WSTEPS = SVB_WCHUNK / 256;
+constexpr int SVB_SEG = SVB_WCHUNK * SVB_WARPS;   // samples per segment (one look-back per segment): 8192
+constexpr int SVB_WDATA = SVB_WCHUNK * 3;         // data bytes of a warp's chunk at most
 constexpr uint32_t SVB_REC_HEAD = 8 + 2 + 4 + 8 * 4 + 8;   // record size, id length, read_group, 4 doubles, signal bytes (+ the id itself)
 // auxiliary fields as set_record_aux_fields writes them (src/gensig.c:185-217): channel_number (uint64 length + "0",
 // slow5lib/src/slow5.c:4005), median_before f64, read_number i32, start_mux u8, start_time u64 (+ end_reason u8 when
@@ -136,238 +141,204 @@ __global__ void __launch_bounds__(1024) svb_layout_kernel(const SvbParams p) {
     }
 }
 
-constexpr unsigned long long SVB_FLAG_AGG = 1ull << 62, SVB_FLAG_PRE = 2ull << 62, SVB_VAL_MASK = (1ull << 62) - 1;
-constexpr int SVB_WARPS = SVB_THREADS / 32;
-constexpr int SVB_WCHUNK = SVB_SEG / SVB_WARPS;       // samples of a segment coded by one warp: 4096 = 16 steps of 256
-constexpr int SVB_WSTEPS = SVB_WCHUNK / 256;
-constexpr int SVB_WSTAGE = 256 * 3 + 32;              // a warp's staging area: one step of data at any alignment
+// what a CTA needs to know about a segment, in one record: one warp per read, lanes over its segments
+__global__ void __launch_bounds__(256) svb_segmap_kernel(const SvbParams p) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= p.n_reads) return;
+    const int64_t s0 = p.seg0[r], s1 = p.seg0[r + 1];
+    const uint32_t n = p.read_siglen[r];
+    const unsigned long long x = (unsigned long long)p.read_sigoff[r];
+    uint4 *rec = reinterpret_cast<uint4 *>(p.seg_read);
+    for (int64_t sg = s0 + lane; sg < s1; sg += 32) {
+        rec[2 * sg] = make_uint4((uint32_t)r, n, (uint32_t)(sg - s0), 0u);
+        rec[2 * sg + 1] = make_uint4((uint32_t)x, (uint32_t)(x >> 32), 0u, 0u);
+    }
+}
 
-// a warp's staged bytes -> global: 16-byte stores where the destination allows, head and tail bytes one by one.
-// src + shift has the alignment (mod 16) of dst.
+constexpr unsigned long long SVB_FLAG_AGG = 1ull << 62, SVB_FLAG_PRE = 2ull << 62, SVB_VAL_MASK = (1ull << 62) - 1;
+
+// bytes hb .. hb+15 of the 32 bytes (a : b), hb in 0..15 (warp-uniform)
+__device__ __forceinline__ uint4 svb_shift16(const uint4 &a, const uint4 &b, uint32_t hb) {
+    const uint32_t q = hb >> 2, sel = 0x3210u + 0x1111u * (hb & 3u);
+    uint32_t w0, w1, w2, w3, w4;
+    if (q == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
+    else if (q == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+    else if (q == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+    else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
+    return make_uint4(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel), __byte_perm(w3, w4, sel));
+}
+
+// a warp's staged bytes (src: 16-byte aligned shared memory, readable 16 bytes past n) -> global, at any alignment of dst:
+// 16-byte stores for the aligned body of dst - the source is read through a byte funnel -, head and tail bytes one by one
 __device__ __forceinline__ void svb_warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
     const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
     if ((uint32_t)lane < head) dst[lane] = src[lane];
     const uint32_t body = (n - head) >> 4;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
     uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
-    for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
+    for (uint32_t i = lane; i < body; i += 32) d4[i] = head ? svb_shift16(s4[i], s4[i + 1], head) : s4[i];
     const uint32_t done = head + (body << 4);
     if (done + lane < n) dst[done + lane] = src[done + lane];
 }
 
 // L2: one segment per CTA iteration, in ticket order
 __global__ void __launch_bounds__(SVB_THREADS) svb_encode_kernel(const SvbParams p) {
-    __shared__ __align__(16) uint8_t s_stage[SVB_WARPS][SVB_WSTAGE];
+    __shared__ __align__(16) uint8_t s_data[SVB_WARPS][SVB_WDATA + 32];
+    __shared__ __align__(16) uint8_t s_keys[SVB_WARPS][SVB_WCHUNK / 4 + 32];
     __shared__ uint32_t s_warp[SVB_WARPS];
-    __shared__ unsigned long long s_part[SVB_WARPS];
     __shared__ unsigned long long s_excl;
-    __shared__ int s_seg, s_read;
+    __shared__ int s_seg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nseg_all = p.seg0[p.n_reads];
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int tk = atomicAdd(p.ticket, 1u);
-            s_seg = (int)tk;
-            // the read of this segment: last r with seg0[r] <= segment
-            int lo = 0, hi = p.n_reads;
-            if ((int64_t)tk < nseg_all) {
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (p.seg0[mid] <= (int64_t)tk) lo = mid; else hi = mid;
-                }
-            }
-            s_read = lo;
-        }
+        if (threadIdx.x == 0) s_seg = (int)atomicAdd(p.ticket, 1u);   // (not taken ahead of time: a ticket held back stalls every look-back behind it)
         __syncthreads();
-        const int seg = s_seg, r = s_read;
+        const int seg = s_seg;
         if ((int64_t)seg >= nseg_all) return;
-        const uint32_t n = p.read_siglen[r];
-        const uint32_t sl = (uint32_t)((int64_t)seg - p.seg0[r]);     // segment within the read
-        const int16_t *x = p.sig + p.read_sigoff[r];
+        // the segment's read, its length, the segment's place in it and the read's place in the arena: one record, one round trip
+        const uint4 m0 = reinterpret_cast<const uint4 *>(p.seg_read)[2 * (size_t)seg], m1 = reinterpret_cast<const uint4 *>(p.seg_read)[2 * (size_t)seg + 1];
+        const int r = (int)m0.x;
+        const uint32_t n = m0.y;
+        const uint32_t sl = m0.z;                                      // segment within the read
+        const int16_t *x = p.sig + (long long)(((unsigned long long)m1.y << 32) | m1.x);
         const uint32_t w_i0 = sl * SVB_SEG + warp * SVB_WCHUNK;      // first sample of this warp's chunk
-        // ---- first sweep: data bytes of the warp's chunk.  (Samples behind the read's end, up to the next multiple of 8,
-        // are arena padding: counted here and there alike, corrected below.) ----
-        uint32_t mine_all = 0;
-        {
-            int32_t prev = (w_i0 && w_i0 < n) ? (int32_t)x[w_i0 - 1] : 0;
-            // four steps at a time, their loads issued together: the sweep is bound by the bytes in flight
-            for (int st0 = 0; st0 < SVB_WSTEPS; st0 += 4) {
-                if (w_i0 + st0 * 256 >= n) break;
-                uint4 qq[4];
+        uint8_t *stage = s_data[warp];
+        // ---- the warp codes its chunk into shared memory: 256 samples per step, all four loads issued first ----
+        uint32_t woff = 0;   // data bytes staged so far (warp-uniform)
+        if (w_i0 < n) {
+            int32_t prev = w_i0 ? (int32_t)x[w_i0 - 1] : 0;
+            uint4 qq[SVB_WSTEPS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i0 = w_i0 + (st0 + u) * 256 + lane * 8;
-                    qq[u] = make_uint4(0, 0, 0, 0);
-                    if (i0 < n) qq[u] = *reinterpret_cast<const uint4 *>(x + i0);
+            for (int st = 0; st < SVB_WSTEPS; st++) {
+                const uint32_t i0 = w_i0 + st * 256 + lane * 8;
+                qq[st] = make_uint4(0, 0, 0, 0);
+                if (i0 < n) qq[st] = *reinterpret_cast<const uint4 *>(x + i0);
+            }
+#pragma unroll
+            for (int st = 0; st < SVB_WSTEPS; st++) {
+                const uint32_t step_i0 = w_i0 + st * 256;
+                if (step_i0 >= n) break;
+                const uint32_t i0 = step_i0 + lane * 8;
+                const uint4 q = qq[st];
+                int32_t pl = __shfl_up_sync(0xffffffffu, svb_last(q), 1);
+                if (lane == 0) pl = prev;
+                prev = __shfl_sync(0xffffffffu, svb_last(q), 31);
+                uint32_t v[8], nb[8];
+                svb_code8(q, pl, v, nb);
+                if (i0 + 8 > n) {       // the read ends inside (or before) this lane's samples
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (i0 + j >= n) { nb[j] = 0; v[j] = 0; }
                 }
+                const uint32_t mine = ((nb[0] + nb[1]) + (nb[2] + nb[3])) + ((nb[4] + nb[5]) + (nb[6] + nb[7]));
+                uint32_t inc = mine;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i0 = w_i0 + (st0 + u) * 256 + lane * 8;
-                    if (w_i0 + (st0 + u) * 256 >= n) break;
-                    const uint4 q = qq[u];
-                    int32_t pl = __shfl_up_sync(0xffffffffu, svb_last(q), 1);
-                    if (lane == 0) pl = prev;
-                    prev = __shfl_sync(0xffffffffu, svb_last(q), 31);
-                    uint32_t v[8], nb[8];
-                    svb_code8(q, pl, v, nb);
-                    if (i0 + 8 <= n) {
-                        mine_all += ((nb[0] + nb[1]) + (nb[2] + nb[3])) + ((nb[4] + nb[5]) + (nb[6] + nb[7]));
-                    } else {
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const uint32_t step_total = __shfl_sync(0xffffffffu, inc, 31);
+                // two key bytes: four 2-bit codes (bytes - 1) each, first value in the low bits; a value behind the end codes 0
+                const uint32_t c0 = nb[0] ? nb[0] - 1 : 0u, c1 = nb[1] ? nb[1] - 1 : 0u, c2 = nb[2] ? nb[2] - 1 : 0u, c3 = nb[3] ? nb[3] - 1 : 0u;
+                const uint32_t c4 = nb[4] ? nb[4] - 1 : 0u, c5 = nb[5] ? nb[5] - 1 : 0u, c6 = nb[6] ? nb[6] - 1 : 0u, c7 = nb[7] ? nb[7] - 1 : 0u;
+                const uint32_t k0 = c0 + 4 * c1 + 16 * c2 + 64 * c3, k1 = c4 + 4 * c5 + 16 * c6 + 64 * c7;
+                *reinterpret_cast<uint16_t *>(&s_keys[warp][st * 64 + 2 * lane]) = (uint16_t)(k0 | (k1 << 8));
+                // data: every value but the lane's last stores two bytes unconditionally (the second is overwritten by the
+                // next value when it has one byte only); third bytes (|delta| >= 2^15: none in any sane signal) by a
+                // branch of their own
+                uint8_t *d = stage + woff + (inc - mine);
+                if (i0 + 8 <= n) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) mine_all += (i0 + j < n) ? nb[j] : 0u;
+                    for (int j = 0; j < 7; j++) {
+                        d[0] = (uint8_t)v[j];
+                        d[1] = (uint8_t)(v[j] >> 8);
+                        d += nb[j];
+                    }
+                    d[0] = (uint8_t)v[7];
+                    if (nb[7] > 1) d[1] = (uint8_t)(v[7] >> 8);
+                    if (((v[0] | v[1] | v[2] | v[3]) | (v[4] | v[5] | v[6] | v[7])) >> 16) {   // some value has three bytes
+                        d = stage + woff + (inc - mine);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            if (nb[j] > 2) d[2] = (uint8_t)(v[j] >> 16);
+                            d += nb[j];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (nb[j] > 0) d[0] = (uint8_t)v[j];
+                        if (nb[j] > 1) d[1] = (uint8_t)(v[j] >> 8);
+                        if (nb[j] > 2) d[2] = (uint8_t)(v[j] >> 16);
+                        d += nb[j];
                     }
                 }
+                woff += step_total;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mine_all += __shfl_xor_sync(0xffffffffu, mine_all, o);
-        if (lane == 0) s_warp[warp] = mine_all;
+        if (lane == 0) s_warp[warp] = woff;
         __syncthreads();
-        // ---- decoupled look-back by the whole CTA: data bytes of all segments before this one.  Thread t looks at
-        // segment j - t; the window ends at the nearest published PREFIX (everything nearer must at least have published
-        // its AGGREGATE, else the window is read again) ----
+        // ---- decoupled look-back by warp 0: data bytes of all segments before this one.  Lane l looks at segment j - l; the
+        // window ends at the nearest published PREFIX (everything nearer must at least have published its AGGREGATE, else
+        // the window is read again after a short sleep); the other warps wait at the barrier below.  The status words are
+        // published by reductions without a return value (RED: sent and forgotten, yet performed at L2 at once - plain stores
+        // measured slower to become visible) and without a fence: a word carries its value ----
         uint32_t seg_total = 0, warp_before = 0;
 #pragma unroll
         for (int w = 0; w < SVB_WARPS; w++) {
             if (w < warp) warp_before += s_warp[w];
             seg_total += s_warp[w];
         }
-        __syncthreads();   // (s_warp is reused below)
-        {
+        if (warp == 0) {
             unsigned long long excl = 0;
+            volatile unsigned long long *state = reinterpret_cast<volatile unsigned long long *>(p.seg_state);
             if (seg > 0) {
-                if (threadIdx.x == 0) atomicExch(p.seg_state + seg, SVB_FLAG_AGG | (unsigned long long)seg_total);
-                int j = seg - 1;        // window: segments j, j-1, .., j-255
+                if (lane == 0) atomicAdd(p.seg_state + seg, SVB_FLAG_AGG | (unsigned long long)seg_total);   // (the word was zero; no value returned: a reduction, sent and forgotten)
+                int j = seg - 1;        // window: segments j, j-1, .., j-31
                 for (;;) {
-                    const int mine = j - (int)threadIdx.x;
+                    const int mine = j - lane;
                     unsigned long long w = SVB_FLAG_PRE;       // (before segment 0: a prefix of nothing)
-                    if (mine >= 0) w = *reinterpret_cast<volatile unsigned long long *>(p.seg_state + mine);
+                    if (mine >= 0) w = state[mine];
                     const unsigned int st = (unsigned int)(w >> 62);
-                    // nearest prefix = lowest thread index holding one; all threads below it must be ready
                     const unsigned int pre_b = __ballot_sync(0xffffffffu, st == 2), rdy_b = __ballot_sync(0xffffffffu, st != 0);
-                    if (lane == 0) s_warp[warp] = pre_b ? (uint32_t)(__ffs(pre_b) - 1) | ((~rdy_b & ((pre_b & -pre_b) - 1u)) ? 0x100u : 0u)
-                                                        : 0x80u | (rdy_b != 0xFFFFFFFFu ? 0x100u : 0u);
-                    __syncthreads();
-                    int first_pre = -1;
-                    bool retry = false;
-#pragma unroll
-                    for (int ww = 0; ww < SVB_WARPS; ww++) {
-                        const uint32_t e = s_warp[ww];
-                        if (first_pre < 0) {
-                            if (e & 0x100u) retry = true;           // a segment in front of the prefix is not published yet
-                            if (!(e & 0x80u)) first_pre = 32 * ww + (int)(e & 31u);
-                        }
+                    const unsigned int nearer = pre_b ? ((pre_b & (0u - pre_b)) - 1u) : 0xFFFFFFFFu;   // lanes in front of the nearest prefix
+                    if (~rdy_b & nearer) {   // one of them has not published yet
+                        __nanosleep(40);
+                        continue;
                     }
-                    __syncthreads();
-                    if (retry) continue;
-                    const int upto = first_pre < 0 ? SVB_THREADS - 1 : first_pre;
-                    unsigned long long part = ((int)threadIdx.x <= upto) ? (w & SVB_VAL_MASK) : 0ull;
+                    unsigned long long part = (((nearer << 1) | 1u) >> lane) & 1u ? (w & SVB_VAL_MASK) : 0ull;   // lanes up to and incl. the prefix
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                    if (lane == 0) s_part[warp] = part;
-                    __syncthreads();
-#pragma unroll
-                    for (int ww = 0; ww < SVB_WARPS; ww++) excl += s_part[ww];
-                    __syncthreads();
-                    if (first_pre >= 0) break;
-                    j -= SVB_THREADS;
+                    excl += part;
+                    if (pre_b) break;
+                    j -= 32;
                 }
             }
-            if (threadIdx.x == 0) {
+            if (lane == 0) {
+                s_excl = excl;
+                // AGGREGATE | total  ->  PREFIX | excl + total, by one more reduction
+                atomicAdd(p.seg_state + seg, seg > 0 ? (SVB_FLAG_PRE - SVB_FLAG_AGG) + excl : SVB_FLAG_PRE | (unsigned long long)seg_total);
                 p.seg_excl[seg] = excl;
                 if ((int64_t)seg == nseg_all - 1) p.seg_excl[nseg_all] = excl + seg_total;
                 if (sl == 0) *reinterpret_cast<volatile unsigned long long *>(p.read_d0 + r) = excl;
-                __threadfence();
-                atomicExch(p.seg_state + seg, SVB_FLAG_PRE | (excl + seg_total));
-                s_excl = excl;
             }
         }
         __syncthreads();
         const unsigned long long excl = s_excl;
         if (w_i0 >= n) continue;   // (this warp's chunk lies behind the read's end)
-        // keys of the segment lie at (start of the read's key area) + 8192 sl.  The key area ends where the read's data area
+        // keys of the segment lie at (start of the read's key area) + 2048 sl.  The key area ends where the read's data area
         // starts: fixed[r] + (data bytes of the READS before) - a value its first segment publishes (that segment holds
         // an earlier ticket: it is running or done)
         unsigned long long d0 = excl;
         if (sl != 0) {
             do { d0 = *reinterpret_cast<volatile unsigned long long *>(p.read_d0 + r); } while (d0 == ~0ull);
         }
-        uint8_t *keys_dst = p.out + p.fixed[r] + d0 - (uint64_t)((n + 3) / 4) + (uint64_t)(w_i0 / 4) + 2 * lane;
-        uint8_t *data_dst = p.out + p.fixed[r] + excl + warp_before;
-        uint8_t *stage = s_stage[warp];
-        // ---- second sweep: the warp codes its chunk, 256 samples at a time, through its own staging area; no CTA barrier ----
-        int32_t prev = w_i0 ? (int32_t)x[w_i0 - 1] : 0;
-        uint4 qn = make_uint4(0, 0, 0, 0);
-        if (w_i0 + lane * 8 < n) qn = *reinterpret_cast<const uint4 *>(x + w_i0 + lane * 8);
-        for (int st = 0; st < SVB_WSTEPS; st++) {
-            const uint32_t step_i0 = w_i0 + st * 256;
-            if (step_i0 >= n) break;
-            const uint32_t i0 = step_i0 + lane * 8;
-            const uint4 q = qn;
-            qn = make_uint4(0, 0, 0, 0);
-            if (st + 1 < SVB_WSTEPS && i0 + 256 < n) qn = *reinterpret_cast<const uint4 *>(x + i0 + 256);
-            int32_t pl = __shfl_up_sync(0xffffffffu, svb_last(q), 1);
-            if (lane == 0) pl = prev;
-            prev = __shfl_sync(0xffffffffu, svb_last(q), 31);
-            uint32_t v[8], nb[8];
-            svb_code8(q, pl, v, nb);
-            if (i0 + 8 > n) {       // the read ends inside (or before) this lane's samples
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (i0 + j >= n) { nb[j] = 0; v[j] = 0; }
-            }
-            const uint32_t mine = ((nb[0] + nb[1]) + (nb[2] + nb[3])) + ((nb[4] + nb[5]) + (nb[6] + nb[7]));
-            uint32_t inc = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            const uint32_t step_total = __shfl_sync(0xffffffffu, inc, 31);
-            // two key bytes: four 2-bit codes (bytes - 1) each, first value in the low bits; a value behind the end codes 0
-            const uint32_t c0 = nb[0] ? nb[0] - 1 : 0u, c1 = nb[1] ? nb[1] - 1 : 0u, c2 = nb[2] ? nb[2] - 1 : 0u, c3 = nb[3] ? nb[3] - 1 : 0u;
-            const uint32_t c4 = nb[4] ? nb[4] - 1 : 0u, c5 = nb[5] ? nb[5] - 1 : 0u, c6 = nb[6] ? nb[6] - 1 : 0u, c7 = nb[7] ? nb[7] - 1 : 0u;
-            const uint32_t k0 = c0 + 4 * c1 + 16 * c2 + 64 * c3, k1 = c4 + 4 * c5 + 16 * c6 + 64 * c7;
-            if (i0 < n) keys_dst[0] = (uint8_t)k0;
-            if (i0 + 4 < n) keys_dst[1] = (uint8_t)k1;
-            keys_dst += 64;
-            // data: the lane's bytes into the staging area at the alignment (mod 16) of the destination.  Every value
-            // but the lane's last stores two bytes unconditionally (the second is overwritten by the next value when it
-            // has one byte only); third bytes (|delta| >= 2^15: none in any sane signal) by a branch of their own.
-            const uint32_t dshift = (uint32_t)(reinterpret_cast<uintptr_t>(data_dst) & 15);
-            uint8_t *d = stage + dshift + (inc - mine);
-            __syncwarp();   // (the previous step's staged bytes have been copied out)
-            if (i0 + 8 <= n) {
-#pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    d[0] = (uint8_t)v[j];
-                    d[1] = (uint8_t)(v[j] >> 8);
-                    d += nb[j];
-                }
-                d[0] = (uint8_t)v[7];
-                if (nb[7] > 1) d[1] = (uint8_t)(v[7] >> 8);
-                if (((v[0] | v[1] | v[2] | v[3]) | (v[4] | v[5] | v[6] | v[7])) >> 16) {   // some value has three bytes
-                    d = stage + dshift + (inc - mine);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        if (nb[j] > 2) d[2] = (uint8_t)(v[j] >> 16);
-                        d += nb[j];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (nb[j] > 0) d[0] = (uint8_t)v[j];
-                    if (nb[j] > 1) d[1] = (uint8_t)(v[j] >> 8);
-                    if (nb[j] > 2) d[2] = (uint8_t)(v[j] >> 16);
-                    d += nb[j];
-                }
-            }
-            __syncwarp();
-            svb_warp_copy(data_dst, stage + dshift, step_total, lane);
-            data_dst += step_total;
-        }
+        // ---- copy out: this warp's keys and data bytes ----
+        const uint32_t nkeys_w = (min(n - w_i0, (uint32_t)SVB_WCHUNK) + 3) / 4;
+        svb_warp_copy(p.out + p.fixed[r] + d0 - (uint64_t)((n + 3) / 4) + (uint64_t)(w_i0 / 4), s_keys[warp], nkeys_w, lane);
+        svb_warp_copy(p.out + p.fixed[r] + excl + warp_before, stage, woff, lane);
     }
 }
 
