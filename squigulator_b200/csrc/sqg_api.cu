@@ -742,7 +742,9 @@ int slot_compress(sqg_ctx *ctx, Slot &s) {
     CU(cudaMemsetAsync(s.d_read_d0.p, 0xFF, n * sizeof(unsigned long long), s.stream));
     svb_layout_kernel<<<1, 1024, 0, s.stream>>>(q);
     svb_segmap_kernel<<<(int)((n + 7) / 8), 256, 0, s.stream>>>(q);
-    svb_encode_kernel<<<ctx->num_sms * 8, SVB_THREADS, 0, s.stream>>>(q);
+    int svb_ctas = 8;   // CTAs per SM launched (persistent by ticket; five are resident at 48 registers: measured 2/3/4/5 resident = 1.36/1.06/0.92/0.85 ms, six with spills 0.90)
+    if (const char *e = getenv("SQG_SVB_CTAS")) svb_ctas = std::max(1, atoi(e));   // (experiments)
+    svb_encode_kernel<<<ctx->num_sms * svb_ctas, SVB_THREADS, 0, s.stream>>>(q);
     svb_finish_kernel<<<(int)((n + 7) / 8), 256, 0, s.stream>>>(q);
     if (records) svb_start_time_kernel<<<1, 1024, 0, s.stream>>>(q);
     publish_kernel<<<1, 32, 0, s.stream>>>(s.d_svb_tot.p, 1, nullptr, 0, s.h_svb_tot.p);
@@ -1070,6 +1072,8 @@ int ctx_device_setup(sqg_ctx *ctx, const sqg_model_t *h_model, const void *d_mod
     }
 
     CU(cudaFuncSetAttribute((const void *)dwell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+    // the svb-zd encoder stages a segment per CTA in (static) shared memory: let the SM carve out what 6-8 resident CTAs need
+    CU(cudaFuncSetAttribute((const void *)svb_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     k4_fn fn = pick_k4(ctx->noisy, ctx->rand_dwell, ctx->meth, ctx->rev);
     if (SM_TOTAL > prop.sharedMemPerBlockOptin) return fail(ctx, SQG_ERR_CUDA, "signal kernel: shared-memory layout does not fit");
     {
