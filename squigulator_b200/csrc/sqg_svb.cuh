@@ -56,7 +56,10 @@ struct SvbParams {
     int32_t ont_friendly;        // an end_reason byte follows (src/gensig.c:158-166, :211-217)
 };
 
-constexpr int SVB_THREADS = 256;
+#ifndef SQG_SVB_THREADS
+#define SQG_SVB_THREADS 256
+#endif
+constexpr int SVB_THREADS = SQG_SVB_THREADS;
 constexpr int SVB_WARPS = SVB_THREADS / 32;
 constexpr int SVB_WCHUNK = 1024;                  // samples of a segment coded by one warp: 4 steps of 256 (8 per lane)
 constexpr int SVB_WSTEPS = SVB_WCHUNK / 256;
