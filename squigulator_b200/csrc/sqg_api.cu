@@ -147,7 +147,6 @@ struct Slot {
     PinBuf<PieceRef> h_pieces;
     DevBuf<int64_t> d_out_off;
     DevBuf<uint64_t> d_cg_count, d_cg_off;
-    DevBuf<unsigned char> d_scan_tmp;
     PinBuf<int64_t> h_base_off;
     PinBuf<uint64_t> h_cg;
     PinBuf<char> h_bases;
@@ -183,7 +182,7 @@ struct Slot {
         d_read_d0.release(); d_ticket.release(); d_ids.release(); h_svb_tot.release();
         d_sst_len.release(); d_sst_off.release(); d_ss_off.release(); d_sst.release(); h_sst_off.release(); h_sst.release();
         d_pieces.release(); h_pieces.release();
-        d_coords.release(); d_out_off.release(); d_cg_count.release(); d_cg_off.release(); d_scan_tmp.release();
+        d_coords.release(); d_out_off.release(); d_cg_count.release(); d_cg_off.release();
         h_base_off.release(); h_cg.release(); h_bases.release();
         for (auto e : kev) cudaEventDestroy(e);
         kev.clear();
@@ -527,15 +526,15 @@ int slot_extract(sqg_ctx *ctx, Slot &s, const sqg_coord_t *coords, int64_t meth_
     for (int j = 1; j <= 32; j++) q.pw[j] = mulmod31(q.pw[j - 1], LEHMER_A);
     const int grid = (int)((np + EX_THREADS / 32 - 1) / (EX_THREADS / 32));
     extract_count_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
-    size_t tmp = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, q.cnt, q.cnt_off, (int)np, s.stream));
-    CU(s.d_scan_tmp.ensure(tmp + 16, false, s.stream));
-    CU(cub::DeviceScan::ExclusiveSum(s.d_scan_tmp.p, tmp, q.cnt, q.cnt_off, (int)np, s.stream));
-    publish_kernel<<<1, 32, 0, s.stream>>>(reinterpret_cast<const int64_t *>(q.cnt_off + (np - 1)), 1,
-                                           reinterpret_cast<const int64_t *>(q.cnt + (np - 1)), 1,
-                                           reinterpret_cast<int64_t *>(s.h_cg.p));
+    if (q.do_meth) {   // CpG ordinals run through the batch (rand_meth is one stream); N ordinals restart at every read
+        extract_scan_kernel<<<1, 1024, 0, s.stream>>>(q);
+        publish_kernel<<<1, 32, 0, s.stream>>>(reinterpret_cast<const int64_t *>(q.cnt_off + (np - 1)), 1,
+                                               reinterpret_cast<const int64_t *>(q.cnt + (np - 1)), 1,
+                                               reinterpret_cast<int64_t *>(s.h_cg.p));
+        ctx->launches += 2;
+    }
     extract_reads_kernel<<<grid, EX_THREADS, 0, s.stream>>>(q);
-    ctx->launches += 4;
+    ctx->launches += 2;
     CU(cudaGetLastError());
     return SQG_OK;
 }

@@ -15,8 +15,10 @@
 // sites, one exclusive scan over the pieces of the batch turns the counts into ordinals (N's restart at every read,
 // CpG sites run through the batch), and inside a piece ballot/popcount numbers the hits of each 32-position row.
 // Every output byte is written by the lane that owns its forward position; four rows of loads are in flight per lane.
+// A piece without N's of a read without methylation - nearly every piece of a real genome - needs no stream at all: it
+// is a copy or a reverse complement, done 16 output bytes per lane and step (aligned 16-byte stores, the source read
+// through a byte funnel, the complement as SWAR arithmetic on four bases per register).
 #pragma once
-#include <cub/cub.cuh>
 
 #include "sqg_legacy.cuh"
 
@@ -46,7 +48,7 @@ struct ExtractParams {
     const int64_t *out_off;  // n_reads + 1, relative to `out`
     uint8_t *out;
     uint64_t *cnt;           // per piece: (N's << 32) | CpG sites
-    uint64_t *cnt_off;       // exclusive scan of cnt over the batch's pieces
+    uint64_t *cnt_off;       // exclusive scan of cnt over the batch's pieces (methylation only)
     uint32_t meth_residue;   // (seed + 6) mod m
     uint64_t meth_draw_base;
     int32_t n_pieces, do_meth;
@@ -55,6 +57,33 @@ struct ExtractParams {
 
 __device__ __forceinline__ bool read_has_meth(const ExtractParams &q, const Coord &c) {
     return q.do_meth && q.meth && (!q.contig_has_meth || q.contig_has_meth[c.contig]);
+}
+
+// 16 bytes from any address: five aligned words (the fifth only touched when the address is not a multiple of four: it
+// then holds bytes of the window; the genome buffers end in 64 bytes of padding) through a byte funnel.  x[0] = lowest address.
+__device__ __forceinline__ void ex_load16(const uint8_t *src, uint32_t (&x)[4]) {
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(src - sh);
+    const uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = __ldg(a + 3), w4 = sh ? __ldg(a + 4) : 0u;
+    const uint32_t sel = 0x3210u + 0x1111u * sh;
+    x[0] = __byte_perm(w0, w1, sel); x[1] = __byte_perm(w1, w2, sel); x[2] = __byte_perm(w2, w3, sel); x[3] = __byte_perm(w3, w4, sel);
+}
+// 0x80 in every byte of x that is zero (exact: no borrow travels between bytes)
+__device__ __forceinline__ uint32_t ex_zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+// four bases -> their complements in reverse order (src/seq.h:77-112: ACGTacgt -> TGCA, anything else -> T).  The digit
+// ((c>>1) ^ (c>>2)) & 3 of ACGT is 0 1 2 3 in either case; the digits, as PRMT selectors, pick the complement out of
+// "TGCA" and - to tell the eight letters from every other byte - the letter itself out of "ACGT".
+__device__ __forceinline__ uint32_t ex_revcomp4(uint32_t w) {
+    const uint32_t d = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+    const uint32_t u = (d | (d >> 4)) & 0x00FF00FFu;
+    const uint32_t sel = (u | (u >> 8)) & 0xFFFFu;
+    const uint32_t other = __byte_perm(0x54474341u /* "ACGT" */, 0u, sel) ^ (w & 0xDFDFDFDFu);   // non-zero bytes: not one of the eight
+    uint32_t comp = __byte_perm(0x41434754u /* "TGCA" */, 0u, sel);
+    if (other) {
+        const uint32_t m = (0x80808080u ^ ex_zero_bytes(other)) >> 7;   // 0x01 in those bytes
+        comp = (comp & ~(m * 0xFFu)) | (m * 0x54u);
+    }
+    return __byte_perm(comp, 0u, 0x0123);
 }
 
 // N's and CpG sites per piece (the draws is_bad_read / methylate_dna will take there)
@@ -68,6 +97,29 @@ __global__ void __launch_bounds__(EX_THREADS) extract_count_kernel(const __grid_
     const uint8_t *g = q.genome + q.contig_off[c.contig] + c.pos;
     const bool meth = read_has_meth(q, c);
     uint32_t nn = 0, nc = 0;
+    if (!meth) {
+        // only the N's are wanted: 16 bytes per lane and step, all of a piece's loads in flight at once
+        uint32_t x[XSEG / 512][4];
+#pragma unroll
+        for (int t = 0; t < XSEG / 512; t++) {
+            const int i = lo + 512 * t + 16 * lane;
+            x[t][0] = x[t][1] = x[t][2] = x[t][3] = 0u;
+            if (i < hi) ex_load16(g + i, x[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < XSEG / 512; t++) {
+            const int left = hi - (lo + 512 * t + 16 * lane);   // bytes of this chunk inside the piece
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int nb = min(max(left - 4 * j, 0), 4);
+                const uint32_t valid = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+                nn += __popc(ex_zero_bytes(x[t][j] ^ 0x4E4E4E4Eu) & valid);
+            }
+        }
+        nn = __reduce_add_sync(0xFFFFFFFFu, nn);
+        if (lane == 0) q.cnt[s] = (uint64_t)nn << 32;
+        return;
+    }
     for (int i0 = lo; i0 < hi; i0 += 32 * EX_ROWS) {
         uint8_t raw[EX_ROWS];
 #pragma unroll
@@ -85,6 +137,63 @@ __global__ void __launch_bounds__(EX_THREADS) extract_count_kernel(const __grid_
     nn = __reduce_add_sync(0xFFFFFFFFu, nn);
     nc = __reduce_add_sync(0xFFFFFFFFu, nc);
     if (lane == 0) q.cnt[s] = ((uint64_t)nn << 32) | nc;
+}
+
+// exclusive scan of the pieces' packed counts (N's << 32 | CpG sites; both totals stay below 2^32: a batch has fewer
+// than 2^32 bases): one CTA, sixteen consecutive pieces per thread and round (eight 16-byte loads in flight per thread;
+// the kernel is one CTA: nothing else hides the latency)
+constexpr int EX_SCAN_ITEMS = 16;
+__global__ void __launch_bounds__(1024) extract_scan_kernel(const __grid_constant__ ExtractParams q) {
+    __shared__ uint64_t s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t carry = 0;
+    for (int i0 = 0; i0 < q.n_pieces; i0 += 1024 * EX_SCAN_ITEMS) {
+        const int i = i0 + EX_SCAN_ITEMS * tid;
+        uint64_t v[EX_SCAN_ITEMS];
+        if (i + EX_SCAN_ITEMS <= q.n_pieces) {
+#pragma unroll
+            for (int j = 0; j < EX_SCAN_ITEMS; j += 2) {   // (cudaMalloc'd, i a multiple of 16)
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(q.cnt + i + j);
+                v[j] = t.x; v[j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EX_SCAN_ITEMS; j++) v[j] = i + j < q.n_pieces ? q.cnt[i + j] : 0ull;
+        }
+        uint64_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < EX_SCAN_ITEMS; j++) mine += v[j];
+        uint64_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncthreads();   // (the totals of the previous round have been read)
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint64_t before = 0, all = 0;
+#pragma unroll 8
+        for (int w = 0; w < 32; w++) {
+            if (w < warp) before += s_w[w];
+            all += s_w[w];
+        }
+        uint64_t run = carry + before + inc - mine;
+        if (i + EX_SCAN_ITEMS <= q.n_pieces) {
+#pragma unroll
+            for (int j = 0; j < EX_SCAN_ITEMS; j += 2) {
+                *reinterpret_cast<ulonglong2 *>(q.cnt_off + i + j) = make_ulonglong2(run, run + v[j]);
+                run += v[j] + v[j + 1];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EX_SCAN_ITEMS; j++) {
+                if (i + j < q.n_pieces) q.cnt_off[i + j] = run;
+                run += v[j];
+            }
+        }
+        carry += all;
+    }
 }
 
 __device__ __forceinline__ uint8_t complement_base(uint8_t b) {  // src/seq.h:77-101
@@ -116,10 +225,53 @@ __global__ void __launch_bounds__(EX_THREADS) extract_reads_kernel(const __grid_
     uint8_t *out = q.out + q.out_off[pr.read];
     const bool neg = c.strand == '-';
     const bool meth = read_has_meth(q, c);
+    if (!meth && q.cnt[s] == 0) {
+        // ---- no N, no methylation: out[lo..hi) = g[lo..hi), or out[len-hi..len-lo) = the reverse complement of it ----
+        const int o_lo = neg ? len - hi : lo, n = hi - lo;
+        uint8_t *dst = out + o_lo;
+        const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+        const int body = (n - head) >> 4;
+        auto one = [&](int o) {   // output byte o of the read, by itself
+            if (!neg) out[o] = g[o];
+            else out[o] = complement_base(g[len - 1 - o]);
+        };
+        if (lane < head) one(o_lo + lane);
+        for (int c0 = 0; c0 < body; c0 += 128) {
+            uint32_t x[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int ci = c0 + 32 * t + lane;
+                const int o = o_lo + head + 16 * ci;
+                if (ci < body) ex_load16(neg ? g + (len - 16 - o) : g + o, x[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int ci = c0 + 32 * t + lane;
+                if (ci < body) {
+                    uint4 v;
+                    if (!neg) v = make_uint4(x[t][0], x[t][1], x[t][2], x[t][3]);
+                    else v = make_uint4(ex_revcomp4(x[t][3]), ex_revcomp4(x[t][2]), ex_revcomp4(x[t][1]), ex_revcomp4(x[t][0]));
+                    *reinterpret_cast<uint4 *>(dst + head + 16 * ci) = v;
+                }
+            }
+        }
+        const int done = head + 16 * body;
+        if (done + lane < n) one(o_lo + done + lane);
+        return;
+    }
     const uint32_t lt = (1u << lane) - 1;
     // stream positions at the start of the piece; the states themselves are computed at the first hit
-    const uint64_t n_before = (q.cnt_off[s] >> 32) - (q.cnt_off[s - pr.k] >> 32);
-    const uint64_t m_before = q.meth_draw_base + (q.cnt_off[s] & 0xFFFFFFFFu);
+    // (the N's restart at every read: without methylation the batch-wide scan is not run at all, and a piece that does
+    //  hold N's adds up the counts of its read's earlier pieces itself)
+    uint64_t n_before = 0, m_before = 0;
+    if (q.do_meth) {
+        n_before = (q.cnt_off[s] >> 32) - (q.cnt_off[s - pr.k] >> 32);
+        m_before = q.meth_draw_base + (q.cnt_off[s] & 0xFFFFFFFFu);
+    } else {
+        uint32_t nb = 0;
+        for (int j = lane; j < pr.k; j += 32) nb += (uint32_t)(q.cnt[s - pr.k + j] >> 32);
+        n_before = __reduce_add_sync(0xFFFFFFFFu, nb);
+    }
     uint32_t xn = 0, xm = 0;
     bool have_xn = false, have_xm = false;
     bool carry = false;  // '-' reads: the site at the previous position (previous row / previous piece) was marked

@@ -159,6 +159,37 @@ def test_coords_batch_equals_oracle_and_host_path(oracle_lib, meth):
 
 
 @pytest.mark.gpu
+def test_coords_pieces_without_n_take_the_vector_path(oracle_lib):
+    """pieces without N of reads without methylation are copied / reverse-complemented 16 bytes per lane: every
+    alignment of source and destination, lengths around the 16-byte and 2048-position boundaries, lower case and IUPAC
+    letters (complement: T, src/seq.h:77-101), next to pieces that do hold N's (the per-byte path) in the same batch"""
+    import squigulator_b200 as sq
+    from squigulator_b200 import api
+    rs = np.random.RandomState(77)
+    ln = 30000
+    a = np.frombuffer(b"ACGT", dtype=np.uint8)[rs.randint(0, 4, ln)].copy()
+    a[1000:1400] |= 0x20
+    a[rs.randint(0, ln, 40)] = np.frombuffer(b"RYKMSWBDHVUacgtnryk", dtype=np.uint8)[rs.randint(0, 19, 40)]
+    a[20000:20010] = ord("N")   # only pieces covering these take the per-byte path
+    b = np.frombuffer(b"ACGT", dtype=np.uint8)[rs.randint(0, 4, 5000)].copy()
+    contigs = [a.tobytes(), b.tobytes()]
+    coords = []
+    for pos in list(range(0, 20)) + [4093, 4094, 4095, 4096, 4097]:
+        for n in (0, 1, 15, 16, 17, 31, 32, 33, 47, 100, 2047, 2048, 2049, 2063, 2064, 2065, 4096, 5000):
+            for st in "+-":
+                coords.append((0, pos, n, st))
+    coords += [(0, 0, ln, "+"), (0, 0, ln, "-"), (0, 13, ln - 13, "-"), (1, 0, 5000, "-"), (1, 1, 4999, "+"), (0, 19000, 3000, "-"), (0, 19990, 25, "+")]
+    g = sq.SignalGenerator("dna-r9-prom", H.random_model(4 ** 6, seed=5), 6, seed=3)
+    g.load_genome(contigs)
+    out, draws = g.gen_batch_coords(coords, want=api.WANT_BASES)
+    assert draws == 0
+    for i, (c, pos, n, strand) in enumerate(coords):
+        want, _ = H.oracle_extract_read(oracle_lib, contigs[c], None, pos, n, strand, None)
+        assert out[i]["bases"] == want, f"read {i}: {coords[i]}"
+    g.close()
+
+
+@pytest.mark.gpu
 def test_coords_golden_reads_through_gpu():
     """the reference's own gen_read() output (golden) out of the GPU extraction, RNA included"""
     import squigulator_b200 as sq
