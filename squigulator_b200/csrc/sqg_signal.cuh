@@ -486,6 +486,7 @@ __device__ __forceinline__ void emit_ready(const GenParams &p, const unsigned ch
                     }
                 }
                 t.cur_c = UNIT_C * u_end;
+                if (!last) break;   // (what is left is less than a unit: it completes with the next tile)
                 continue;
             }
             if (!last) break;   // the unit completes with the next tile
