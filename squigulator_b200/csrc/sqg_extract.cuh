@@ -17,7 +17,7 @@
 // Every output byte is written by the lane that owns its forward position; four rows of loads are in flight per lane.
 // A piece without N's of a read without methylation - nearly every piece of a real genome - needs no stream at all: it
 // is a copy or a reverse complement, done 16 output bytes per lane and step (aligned 16-byte stores, the source read
-// through a byte funnel, the complement as SWAR arithmetic on four bases per register).
+// as aligned 16-byte words through a byte funnel, the complement as SWAR arithmetic on four bases per register).
 #pragma once
 
 #include "sqg_legacy.cuh"
@@ -59,14 +59,26 @@ __device__ __forceinline__ bool read_has_meth(const ExtractParams &q, const Coor
     return q.do_meth && q.meth && (!q.contig_has_meth || q.contig_has_meth[c.contig]);
 }
 
-// 16 bytes from any address: five aligned words (the fifth only touched when the address is not a multiple of four: it
-// then holds bytes of the window; the genome buffers end in 64 bytes of padding) through a byte funnel.  x[0] = lowest address.
+// 16 bytes from any address: the two aligned 16-byte words around them (the second only touched when the address is not a
+// multiple of 16: it then holds bytes of the window or of the 64 bytes of padding the genome buffers end in) through a
+// byte funnel.  The misalignment is the same for every chunk of a piece, i.e. warp-uniform.  x[0] = lowest address.
+template <int Q>
+__device__ __forceinline__ void ex_pick(const uint4 &A, const uint4 &B, uint32_t sel, uint32_t (&x)[4]) {
+    const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[j] = __byte_perm(w[Q + j], w[Q + j + 1], sel);
+}
 __device__ __forceinline__ void ex_load16(const uint8_t *src, uint32_t (&x)[4]) {
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-    const uint32_t *a = reinterpret_cast<const uint32_t *>(src - sh);
-    const uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = __ldg(a + 3), w4 = sh ? __ldg(a + 4) : 0u;
-    const uint32_t sel = 0x3210u + 0x1111u * sh;
-    x[0] = __byte_perm(w0, w1, sel); x[1] = __byte_perm(w1, w2, sel); x[2] = __byte_perm(w2, w3, sel); x[3] = __byte_perm(w3, w4, sel);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4 *a = reinterpret_cast<const uint4 *>(src - sh);
+    const uint4 A = __ldg(a), B = sh ? __ldg(a + 1) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t sel = 0x3210u + 0x1111u * (sh & 3u);
+    switch (sh >> 2) {
+        case 0: ex_pick<0>(A, B, sel, x); break;
+        case 1: ex_pick<1>(A, B, sel, x); break;
+        case 2: ex_pick<2>(A, B, sel, x); break;
+        default: ex_pick<3>(A, B, sel, x); break;
+    }
 }
 // 0x80 in every byte of x that is zero (exact: no borrow travels between bytes)
 __device__ __forceinline__ uint32_t ex_zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
