@@ -190,6 +190,42 @@ def test_coords_pieces_without_n_take_the_vector_path(oracle_lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("meth", [False, True])
+def test_rank_shards_through_the_library_equal_one_job(meth):
+    """the N-rank decomposition run through libsqg itself: every rank's shard of a coordinate job -
+    first_read_index = its first global read, meth_draw_base from the host-side CpG prefix index, no exchange between
+    ranks - gives the bytes, signals and per-read draws of the one-job call; so does the host-bases path per shard"""
+    import squigulator_b200 as sq
+    from squigulator_b200 import api
+    from squigulator_b200.shard import shard_range, CpgIndex
+    k = 6
+    contigs, marr = H.synthetic_genome(seed=41, n_contigs=4, mean_len=5000)
+    coords = _coords(contigs, 101, seed=9, min_len=40)
+    g = sq.SignalGenerator("dna-r9-prom", H.random_model((5 if meth else 4) ** k, seed=6), k, seed=17, meth=meth)
+    g.load_genome(contigs, meth=marr if meth else None)
+    first = 5000
+    whole, draws = g.gen_batch_coords(coords, first_read_index=first, want=api.WANT_BASES)
+    bases = CpgIndex(contigs).draw_bases(coords) if meth else np.zeros(len(coords) + 1, dtype=np.int64)
+    assert int(bases[-1]) == draws
+    for world in (2, 3):
+        got = []
+        for rank in range(world):
+            lo, hi = shard_range(len(coords), rank, world)
+            part, d = g.gen_batch_coords(coords[lo:hi], first_read_index=first + lo, meth_draw_base=int(bases[lo]), want=api.WANT_BASES)
+            assert d == int(bases[hi] - bases[lo])
+            # the same shard with its bases handed over by the host
+            again = g.gen_batch([o["bases"] for o in part], first_read_index=first + lo)
+            for a, b in zip(part, again):
+                np.testing.assert_array_equal(a["sig"], b["sig"])
+            got += part
+        assert len(got) == len(whole)
+        for a, b in zip(got, whole):
+            assert a["bases"] == b["bases"] and a["offset"] == b["offset"] and a["median_before"] == b["median_before"]
+            np.testing.assert_array_equal(a["sig"], b["sig"])
+    g.close()
+
+
+@pytest.mark.gpu
 def test_coords_golden_reads_through_gpu():
     """the reference's own gen_read() output (golden) out of the GPU extraction, RNA included"""
     import squigulator_b200 as sq
